@@ -1,0 +1,202 @@
+/* b200icp.h -- C ABI of the B200-native ICP scan-registration path.
+ *
+ * This is the drop-in boundary for the ICP seam that mola::LidarOdometry
+ * drives (reference: src/LidarOdometry.cpp).  Each entry point names the
+ * reference interface it replaces.  Plain pointers and sizes only; all device
+ * memory, streams and kernels (sm_100a) live behind the opaque handles.
+ * There is no CPU fallback: every call fails with B200ICP_ERR_CUDA when no
+ * CUDA device / kernel image is usable.
+ *
+ * Threading (reference: LidarOdometry.h:167-172, cpp:94-96, 711-729 -- one
+ * shared ICP object, align() called concurrently from pool threads):
+ *   b200icp_align / _align_batch / _knn / _match / _voxel_decimate are
+ *   re-entrant on one b200icp_t (per-call workspace + stream from a pool);
+ *   handles are immutable after creation.
+ */
+#ifndef B200ICP_H
+#define B200ICP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ICP_INVALID_IDX 0xFFFFFFFFu
+#define B200ICP_MAX_KNN 8
+
+enum
+{
+    B200ICP_OK = 0,
+    B200ICP_ERR_BAD_ARG = -1,
+    B200ICP_ERR_CUDA = -2,
+    B200ICP_ERR_YAML = -3,
+    B200ICP_ERR_UNSUPPORTED = -4,
+    B200ICP_ERR_NOMEM = -5
+};
+
+/* mp2p_icp::IterTermReason, logged as an integer at LidarOdometry.cpp:888.
+ * Numeric values frozen here. */
+enum
+{
+    B200ICP_TERM_UNDEFINED = 0,
+    B200ICP_TERM_NO_PAIRINGS = 1,
+    B200ICP_TERM_SOLVER_ERROR = 2,
+    B200ICP_TERM_MAX_ITERATIONS = 3,
+    B200ICP_TERM_STALLED = 4
+};
+
+enum { B200ICP_SOLVER_GAUSS_NEWTON = 0, B200ICP_SOLVER_HORN = 1 };
+enum { B200ICP_MATCHER_POINT2PLANE = 0, B200ICP_MATCHER_POINTS_DISTANCE = 1 };
+
+/* What load_icp_set_of_params() builds from one ICP YAML block
+ * (LidarOdometry.cpp:57-88): mp2p_icp::Parameters::load_from (cpp:78),
+ * initialize_solvers (cpp:81), initialize_matchers (cpp:84),
+ * initialize_quality_evaluators (cpp:87).  Keys: params/icp-settings-regular.yaml:7-46. */
+typedef struct b200icp_params
+{
+    uint32_t max_iterations;     /* params.maxIterations */
+    double   min_abs_step_trans; /* params.minAbsStep_trans */
+    double   min_abs_step_rot;   /* params.minAbsStep_rot */
+    int32_t  use_scale_outlier_detector;
+    double   scale_outlier_threshold;
+    int32_t  use_robust_kernel;
+    double   robust_kernel_param; /* radians here, degrees in the YAML */
+    double   robust_kernel_scale;
+    int32_t  solver_kind;           /* solvers[0].class */
+    uint32_t solver_max_iterations; /* solvers[0].params.maxIterations */
+    double   gn_min_delta;          /* optional solvers[0].params.minDelta */
+    int32_t  matcher_kind;          /* matchers[0].class */
+    double   distance_threshold;
+    double   plane_eigen_threshold;
+    uint32_t knn;
+    uint32_t min_plane_points; /* optional matchers[0].params.minimumPlanePoints */
+    uint32_t run_from_iteration;
+    uint32_t run_up_to_iteration;
+    double   quality_threshold_distance; /* quality[0].params.thresholdDistance */
+    double   cov_fd_step;
+} b200icp_params_t;
+
+/* mp2p_icp::Results as consumed at LidarOdometry.cpp:873-888:
+ * optimal_tf {mean, cov}, quality, nIterations, terminationReason. */
+typedef struct b200icp_result
+{
+    double   pose[6];  /* x y z yaw pitch roll (mrpt::math::TPose3D order) */
+    double   R[9];     /* row-major rotation of the same pose */
+    double   t[3];
+    double   cov[36];  /* row-major, order x y z yaw pitch roll */
+    double   quality;  /* [0,1] */
+    uint32_t n_iterations;
+    uint32_t termination_reason;
+    uint32_t n_pairings; /* of the last matcher run */
+    uint32_t cov_singular;
+} b200icp_result_t;
+
+/* per-kernel device timings, CUDA events on the launching stream */
+typedef struct b200icp_profile
+{
+    uint64_t match_launches;  /* fused transform+kNN+plane-fit+moments kernel */
+    double   match_ms;
+    uint64_t match_queries;   /* queries processed by those launches */
+    uint64_t solve_launches;
+    double   solve_ms;
+    uint64_t index_builds;
+    double   index_ms;
+    uint64_t index_points;
+    uint64_t knn_launches;
+    double   knn_ms;
+    uint64_t knn_queries;
+    uint64_t voxel_launches;
+    double   voxel_ms;
+    uint64_t voxel_points;
+    uint64_t total_kernel_launches; /* every kernel this library launched */
+} b200icp_profile_t;
+
+typedef struct b200icp       b200icp_t;       /* the mp2p_icp::ICP object + its Parameters */
+typedef struct b200icp_cloud b200icp_cloud_t; /* one point layer of a metric_map_t, resident in HBM */
+
+/* thread-local message of the last failing call on this thread */
+const char* b200icp_last_error(void);
+/* number of usable CUDA devices (0 => every other call fails) */
+int b200icp_device_count(void);
+
+/* --- ICP object (LidarOdometry.cpp:57-88) -------------------------------- */
+void b200icp_default_params(b200icp_params_t* p);
+/* Parses the text of one ICP settings block (icp_class / params / solvers /
+ * matchers / quality). Unknown icp_class / class names fail like cpp:70-75. */
+int b200icp_params_from_yaml(const char* yaml_text, b200icp_params_t* out);
+int b200icp_create(const b200icp_params_t* params, int device, b200icp_t** out);
+int b200icp_create_from_yaml(const char* yaml_text, int device, b200icp_t** out);
+void b200icp_destroy(b200icp_t* icp);
+int b200icp_get_params(const b200icp_t* icp, b200icp_params_t* out);
+int b200icp_device(const b200icp_t* icp);
+
+/* --- clouds (mp2p_icp::metric_map_t point layer; MRPT CPointsMap SoA) ---- */
+/* Copies n points (host SoA float, any memory; pinned gives async DMA) to
+ * the device and builds the search index there (replaces the lazy nanoflann
+ * kd-tree build).  search_radius <= 0 => the ICP object's matcher threshold. */
+int b200icp_cloud_upload(b200icp_t* icp, const float* x, const float* y, const float* z,
+                         size_t n, float search_radius, b200icp_cloud_t** out);
+/* Same from DEVICE pointers (inputs already resident in HBM). */
+int b200icp_cloud_from_device(b200icp_t* icp, const float* dx, const float* dy, const float* dz,
+                              size_t n, float search_radius, b200icp_cloud_t** out);
+void   b200icp_cloud_free(b200icp_cloud_t* c);
+size_t b200icp_cloud_size(const b200icp_cloud_t* c);
+/* original-order coordinates back to the host */
+int b200icp_cloud_download(const b200icp_cloud_t* c, float* x, float* y, float* z);
+
+/* --- voxel decimation (apply_filter_pipeline, LidarOdometry.cpp:223-224) - */
+/* One point per occupied voxel: the lowest original index (or the voxel mean
+ * with use_average), output ordered by ascending original index.  The result
+ * is a new indexed cloud; keep_idx (optional, capacity n) receives the kept
+ * original indices. */
+int b200icp_voxel_decimate(b200icp_t* icp, const b200icp_cloud_t* in, float resolution,
+                           int use_average, float search_radius, b200icp_cloud_t** out,
+                           uint32_t* keep_idx);
+
+/* --- nearest neighbours (kdTreeNClosestPoint3DIdx behind the matchers) --- */
+/* For each point of `queries` moved by pose (x,y,z,yaw,pitch,roll; NULL =
+ * identity): the k nearest points of `ref` with d2 <= max_dist^2, ascending by
+ * (d2 as float32, index).  Outputs are host arrays [nq*k] in the queries'
+ * ORIGINAL order, padded with B200ICP_INVALID_IDX / +inf.  max_dist must be
+ * positive and finite (radius-capped search). */
+int b200icp_knn(b200icp_t* icp, const b200icp_cloud_t* ref, const b200icp_cloud_t* queries,
+                const double* pose6, uint32_t k, float max_dist, uint32_t* idx_out,
+                float* d2_out);
+
+/* --- matcher at a fixed pose (Matcher_Point2Plane; parity hook) ---------- */
+/* Host outputs in the local cloud's ORIGINAL order: paired[n] (0/1),
+ * nn_idx[n*knn] (after the distance cut, padded INVALID), nn_cnt[n],
+ * centroid[n*3], normal[n*3] (f64).  Any output may be NULL. */
+int b200icp_match(b200icp_t* icp, const b200icp_cloud_t* from_global,
+                  const b200icp_cloud_t* to_local, const double* pose6, uint8_t* paired,
+                  uint32_t* nn_idx, uint32_t* nn_cnt, double* centroid, double* normal,
+                  uint32_t* n_pairings);
+
+/* --- registration (mp2p_icp::ICP::align, LidarOdometry.cpp:869-871) ------ */
+/* from = global / reference cloud, to = local cloud moved by the pose;
+ * guess = init_guess_to_wrt_from.  The whole iteration loop runs on the
+ * device; one result struct comes back. */
+int b200icp_align(b200icp_t* icp, const b200icp_cloud_t* from_global,
+                  const b200icp_cloud_t* to_local, const double guess6[6],
+                  b200icp_result_t* out);
+/* n independent registrations in lock-step launches (worker_pool_past_KFs_
+ * jobs cpp:711-729 and the Monte-Carlo loop cpp:775-787). Cloud handles may
+ * repeat (their indices are shared). guesses = [n*6]. */
+int b200icp_align_batch(b200icp_t* icp, size_t n, const b200icp_cloud_t* const* from_global,
+                        const b200icp_cloud_t* const* to_local, const double* guesses6,
+                        b200icp_result_t* out);
+
+/* --- measurement --------------------------------------------------------- */
+void b200icp_profile_enable(b200icp_t* icp, int enable);
+void b200icp_profile_reset(b200icp_t* icp);
+void b200icp_profile_get(b200icp_t* icp, b200icp_profile_t* out);
+/* raw CUstream (as void*) used by the calling thread's next call, so that a
+ * harness can bracket calls with its own events */
+int b200icp_synchronize(b200icp_t* icp);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

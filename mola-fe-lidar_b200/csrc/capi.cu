@@ -1,0 +1,292 @@
+// capi.cu -- extern "C" entry points declared in include/b200icp.h.
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "runtime.cuh"
+
+using namespace b2;
+
+extern "C" const char* b200icp_last_error(void) { return get_error(); }
+
+extern "C" int b200icp_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int b200icp_create(const b200icp_params_t* params, int device, b200icp_t** out)
+{
+    if (!params || !out)
+    {
+        set_error("null argument");
+        return B200ICP_ERR_BAD_ARG;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    B2_CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev)
+    {
+        set_error("CUDA device %d not available (%d devices): this library has no CPU path", device, ndev);
+        return B200ICP_ERR_CUDA;
+    }
+    B2_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    B2_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+    {
+        set_error("device %d is sm_%d%d; this library carries sm_100a kernels only", device, prop.major,
+                  prop.minor);
+        return B200ICP_ERR_CUDA;
+    }
+    // keep freed stream-ordered allocations cached in the pool
+    cudaMemPool_t pool;
+    B2_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;
+    B2_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    auto* ctx = new (std::nothrow) b200icp();
+    if (!ctx) return B200ICP_ERR_NOMEM;
+    ctx->device = device;
+    ctx->P = *params;
+    ctx->sm_count = prop.multiProcessorCount;
+    make_dev_params(ctx->P, ctx->D);
+    memset(&ctx->prof, 0, sizeof(ctx->prof));
+    // first workspace now, so that a broken device fails here
+    Workspace* ws = ctx->acquire();
+    if (!ws)
+    {
+        delete ctx;
+        return B200ICP_ERR_CUDA;
+    }
+    ctx->release(ws);
+    *out = ctx;
+    return B200ICP_OK;
+}
+
+extern "C" int b200icp_create_from_yaml(const char* yaml_text, int device, b200icp_t** out)
+{
+    b200icp_params_t p;
+    if (int r = b200icp_params_from_yaml(yaml_text, &p)) return r;
+    return b200icp_create(&p, device, out);
+}
+
+extern "C" void b200icp_destroy(b200icp_t* icp)
+{
+    if (!icp) return;
+    for (auto* w : icp->all_ws)
+    {
+        w->destroy();
+        delete w;
+    }
+    delete icp;
+}
+
+extern "C" int b200icp_get_params(const b200icp_t* icp, b200icp_params_t* out)
+{
+    if (!icp || !out) return B200ICP_ERR_BAD_ARG;
+    *out = icp->P;
+    return B200ICP_OK;
+}
+
+extern "C" int b200icp_device(const b200icp_t* icp) { return icp ? icp->device : -1; }
+
+static int upload_common(b200icp_t* icp, const float* x, const float* y, const float* z, size_t n,
+                         float search_radius, cudaMemcpyKind kind, b200icp_cloud_t** out)
+{
+    if (!icp || !out || (n && (!x || !y || !z)))
+    {
+        set_error("null argument");
+        return B200ICP_ERR_BAD_ARG;
+    }
+    *out = nullptr;
+    Lease L(icp);
+    if (!L.ws) return B200ICP_ERR_CUDA;
+    b200icp_cloud* c = nullptr;
+    if (int r = cloud_alloc(icp, L.ws, n, search_radius, &c)) return r;
+    cudaStream_t s = L.ws->stream;
+    if (n)
+    {
+        cudaError_t e = cudaMemcpyAsync(c->dx, x, n * sizeof(float), kind, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->dy, y, n * sizeof(float), kind, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->dz, z, n * sizeof(float), kind, s);
+        // the caller's buffers may be reused as soon as we return
+        if (e == cudaSuccess) e = cudaEventRecord(L.ws->ev[2], s);
+        if (e != cudaSuccess)
+        {
+            set_error("cloud copy failed: %s", cudaGetErrorString(e));
+            b200icp_cloud_free(c);
+            return B200ICP_ERR_CUDA;
+        }
+    }
+    if (int r = cloud_build_index(icp, L.ws, c))
+    {
+        b200icp_cloud_free(c);
+        return r;
+    }
+    if (n)
+    {
+        cudaError_t e = cudaEventSynchronize(L.ws->ev[2]);
+        if (e != cudaSuccess)
+        {
+            set_error("cloud copy failed: %s", cudaGetErrorString(e));
+            b200icp_cloud_free(c);
+            return B200ICP_ERR_CUDA;
+        }
+    }
+    *out = c;
+    return B200ICP_OK;
+}
+
+extern "C" int b200icp_cloud_upload(b200icp_t* icp, const float* x, const float* y, const float* z,
+                                    size_t n, float search_radius, b200icp_cloud_t** out)
+{
+    return upload_common(icp, x, y, z, n, search_radius, cudaMemcpyHostToDevice, out);
+}
+
+extern "C" int b200icp_cloud_from_device(b200icp_t* icp, const float* dx, const float* dy,
+                                         const float* dz, size_t n, float search_radius,
+                                         b200icp_cloud_t** out)
+{
+    return upload_common(icp, dx, dy, dz, n, search_radius, cudaMemcpyDeviceToDevice, out);
+}
+
+extern "C" void b200icp_cloud_free(b200icp_cloud_t* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    if (c->ready) cudaEventSynchronize(c->ready);
+    if (c->slab)
+    {
+        Workspace* ws = c->ctx->acquire();
+        if (ws)
+        {
+            cudaFreeAsync(c->slab, ws->stream);
+            c->ctx->release(ws);
+        }
+        else
+            cudaFree(c->slab);
+    }
+    if (c->ready) cudaEventDestroy(c->ready);
+    delete c;
+}
+
+extern "C" size_t b200icp_cloud_size(const b200icp_cloud_t* c) { return c ? c->n : 0; }
+
+extern "C" int b200icp_cloud_download(const b200icp_cloud_t* c, float* x, float* y, float* z)
+{
+    if (!c || !x || !y || !z)
+    {
+        set_error("null argument");
+        return B200ICP_ERR_BAD_ARG;
+    }
+    if (!c->n) return B200ICP_OK;
+    Lease L(c->ctx);
+    if (!L.ws) return B200ICP_ERR_CUDA;
+    cudaStream_t s = L.ws->stream;
+    B2_CUDA_TRY(cudaStreamWaitEvent(s, c->ready, 0));
+    B2_CUDA_TRY(cudaMemcpyAsync(x, c->dx, c->n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    B2_CUDA_TRY(cudaMemcpyAsync(y, c->dy, c->n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    B2_CUDA_TRY(cudaMemcpyAsync(z, c->dz, c->n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    B2_CUDA_TRY(cudaStreamSynchronize(s));
+    return B200ICP_OK;
+}
+
+extern "C" int b200icp_voxel_decimate(b200icp_t* icp, const b200icp_cloud_t* in, float resolution,
+                                      int use_average, float search_radius, b200icp_cloud_t** out,
+                                      uint32_t* keep_idx)
+{
+    if (!icp || !in || !out)
+    {
+        set_error("null argument");
+        return B200ICP_ERR_BAD_ARG;
+    }
+    *out = nullptr;
+    return run_voxel(icp, in, resolution, use_average, search_radius, out, keep_idx);
+}
+
+extern "C" int b200icp_knn(b200icp_t* icp, const b200icp_cloud_t* ref, const b200icp_cloud_t* queries,
+                           const double* pose6, uint32_t k, float max_dist, uint32_t* idx_out,
+                           float* d2_out)
+{
+    if (!icp || !ref || !queries)
+    {
+        set_error("null argument");
+        return B200ICP_ERR_BAD_ARG;
+    }
+    return run_knn(icp, ref, queries, pose6, k, max_dist, idx_out, d2_out);
+}
+
+extern "C" int b200icp_match(b200icp_t* icp, const b200icp_cloud_t* from_global,
+                             const b200icp_cloud_t* to_local, const double* pose6, uint8_t* paired,
+                             uint32_t* nn_idx, uint32_t* nn_cnt, double* centroid, double* normal,
+                             uint32_t* n_pairings)
+{
+    if (!icp || !from_global || !to_local)
+    {
+        set_error("null argument");
+        return B200ICP_ERR_BAD_ARG;
+    }
+    return run_match(icp, from_global, to_local, pose6, paired, nn_idx, nn_cnt, centroid, normal,
+                     n_pairings);
+}
+
+extern "C" int b200icp_align(b200icp_t* icp, const b200icp_cloud_t* from_global,
+                             const b200icp_cloud_t* to_local, const double guess6[6],
+                             b200icp_result_t* out)
+{
+    if (!icp || !from_global || !to_local || !guess6 || !out)
+    {
+        set_error("null argument");  // ASSERT_(in.from_pc); ASSERT_(in.to_pc) cpp:860-861
+        return B200ICP_ERR_BAD_ARG;
+    }
+    const b200icp_cloud_t* f[1] = {from_global};
+    const b200icp_cloud_t* t[1] = {to_local};
+    return run_align_batch(icp, 1, f, t, guess6, out);
+}
+
+extern "C" int b200icp_align_batch(b200icp_t* icp, size_t n, const b200icp_cloud_t* const* from_global,
+                                   const b200icp_cloud_t* const* to_local, const double* guesses6,
+                                   b200icp_result_t* out)
+{
+    if (!icp || (n && (!from_global || !to_local || !guesses6 || !out)))
+    {
+        set_error("null argument");
+        return B200ICP_ERR_BAD_ARG;
+    }
+    for (size_t i = 0; i < n; i++)
+        if (!from_global[i] || !to_local[i])
+        {
+            set_error("null cloud in job %zu", i);
+            return B200ICP_ERR_BAD_ARG;
+        }
+    return run_align_batch(icp, n, from_global, to_local, guesses6, out);
+}
+
+extern "C" void b200icp_profile_enable(b200icp_t* icp, int enable)
+{
+    if (icp) icp->profile_on = enable != 0;
+}
+extern "C" void b200icp_profile_reset(b200icp_t* icp)
+{
+    if (!icp) return;
+    std::lock_guard<std::mutex> lk(icp->mtx);
+    memset(&icp->prof, 0, sizeof(icp->prof));
+}
+extern "C" void b200icp_profile_get(b200icp_t* icp, b200icp_profile_t* out)
+{
+    if (!icp || !out) return;
+    std::lock_guard<std::mutex> lk(icp->mtx);
+    *out = icp->prof;
+}
+extern "C" int b200icp_synchronize(b200icp_t* icp)
+{
+    if (!icp) return B200ICP_ERR_BAD_ARG;
+    B2_CUDA_TRY(cudaSetDevice(icp->device));
+    B2_CUDA_TRY(cudaDeviceSynchronize());
+    return B200ICP_OK;
+}

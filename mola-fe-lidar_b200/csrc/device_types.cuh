@@ -1,0 +1,91 @@
+// device_types.cuh -- HBM-resident data layout of the ICP path.
+//
+// A cloud (one point layer of the reference's mp2p_icp::metric_map_t, i.e. MRPT
+// CPointsMap SoA float buffers -- SURVEY.md Appendix A.1) lives in HBM as:
+//   x[n], y[n], z[n]      original order (what the caller uploaded)
+//   pts[n_valid] float4   (x, y, z, bitcast original index), sorted by the
+//                         30-bit Morton code of the point's grid cell
+//   rank[n]               original index -> sorted position
+//   hkeys/hvals           open-addressing hash: linear cell key -> [start,end)
+//   GridDev               grid origin / cell size / counts, written on device
+// The uniform grid replaces the lazily built nanoflann kd-tree (row I).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b2
+{
+constexpr uint32_t kInvalid = 0xFFFFFFFFu;
+constexpr uint32_t kEmptyKey = 0xFFFFFFFFu;
+constexpr int kGridBits = 10;  // cells per axis = 1024 (30-bit Morton / linear keys)
+constexpr int kGridMax = (1 << kGridBits) - 1;
+constexpr int kChunk = 128;    // queries per CTA in the matcher kernels
+constexpr int kNumMoments = 74; // 60 (nn x hh) + 12 (r0 n x h) + 1 (r0^2) + 1 (count)
+
+struct GridDev
+{
+    float    ox, oy, oz;  // origin = bbox min of the finite points
+    float    cell;        // cell edge actually used (>= requested)
+    float    inv_cell;
+    float    slack;       // in cell units: guards float rounding in cell assignment
+    uint32_t n_valid;     // finite points (sorted first)
+    uint32_t n_cells;     // occupied cells
+    float    bmin[3], bmax[3];
+    uint32_t pad[2];
+};
+
+struct CloudView
+{
+    const float4*   pts;
+    const uint32_t* rank;
+    const GridDev*  grid;
+    const uint32_t* hkeys;
+    const uint2*    hvals;
+    uint32_t        hshift;  // 32 - log2(capacity)
+    uint32_t        hmask;   // capacity - 1
+    uint32_t        n;       // total points (incl. non-finite)
+};
+
+// One registration job, resident in HBM for the whole iteration loop.
+struct JobDev
+{
+    double   R[9], t[3];          // current solution (to wrt from)
+    double   Rprev[9], tprev[3];  // solution of the previous outer iteration
+    double   M[kNumMoments];      // reduced moments of the last matcher run
+    double   cov[36];
+    uint32_t iter;         // outer iterations completed
+    uint32_t status;       // 0 running, 1 finished
+    uint32_t term_reason;
+    uint32_t n_pairings;
+    uint32_t quality_count;
+    uint32_t cov_singular;
+    uint32_t from_cloud, to_cloud;  // indices into the launch's CloudView table
+    uint32_t inner_iters_total;
+    uint32_t pad;
+};
+
+struct IcpDevParams
+{
+    uint32_t max_iterations;
+    double   min_abs_step_trans, min_abs_step_rot;
+    uint32_t solver_max_iterations;
+    double   gn_min_delta;
+    int32_t  matcher_kind;
+    float    thr;       // (float)distanceThreshold
+    float    thr2;      // thr*thr in float (A.5)
+    double   distance_threshold;
+    double   plane_eigen_threshold;
+    uint32_t knn;
+    uint32_t min_plane_points;
+    uint32_t run_from_iteration, run_up_to_iteration;
+    float    q_thr2;    // quality: (float)thresholdDistance squared in float (A.8)
+    float    q_thr;
+    double   cov_fd_step;
+};
+
+__host__ __device__ inline uint32_t hash_slot(uint32_t key, uint32_t shift)
+{
+    return (key * 2654435761u) >> shift;
+}
+
+}  // namespace b2

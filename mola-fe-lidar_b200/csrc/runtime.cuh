@@ -1,0 +1,141 @@
+// runtime.cuh -- host-side runtime of the library: context (the ICP object),
+// per-call workspaces (stream + scratch, pooled for re-entrancy, see the
+// threading note in include/b200icp.h), error reporting and profiling.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200icp.h"
+#include "device_types.cuh"
+
+namespace b2
+{
+void        set_error(const char* fmt, ...);
+const char* get_error();
+
+#define B2_CUDA_TRY(expr)                                                                    \
+    do                                                                                       \
+    {                                                                                        \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess)                                                               \
+        {                                                                                    \
+            ::b2::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),     \
+                                 __FILE__, __LINE__);                                        \
+            return B200ICP_ERR_CUDA;                                                         \
+        }                                                                                    \
+    } while (0)
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+// carve typed arrays out of one scratch allocation: first pass with base=null
+// to size it, second pass with the real base
+struct Carver
+{
+    char*  base;
+    size_t off = 0;
+    explicit Carver(void* b) : base((char*)b) {}
+    template <typename T>
+    T* take(size_t count)
+    {
+        T* p = base ? (T*)(base + off) : nullptr;
+        off += align_up(count * sizeof(T));
+        return p;
+    }
+};
+
+struct Workspace
+{
+    int          device = 0;
+    cudaStream_t stream = nullptr;
+    void*        d_scratch = nullptr;
+    size_t       d_bytes = 0;
+    void*        h_pinned = nullptr;
+    size_t       h_bytes = 0;
+    cudaEvent_t  ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> prof_ev;  // pairs
+    uint64_t     launches = 0;
+
+    int  init(int dev);
+    void destroy();
+    int  reserve_device(size_t bytes);
+    int  reserve_pinned(size_t bytes);
+    int  reserve_prof_events(size_t pairs);
+};
+
+}  // namespace b2
+
+struct b200icp
+{
+    int                                device = 0;
+    b200icp_params_t                   P;
+    b2::IcpDevParams              D;
+    std::mutex                         mtx;
+    std::vector<b2::Workspace*>   free_ws;
+    std::vector<b2::Workspace*>   all_ws;
+    bool                               profile_on = false;
+    b200icp_profile_t                  prof;
+    int                                sm_count = 148;
+
+    b2::Workspace* acquire();
+    void                release(b2::Workspace* ws);
+};
+
+struct b200icp_cloud
+{
+    b200icp* ctx = nullptr;
+    size_t   n = 0;
+    void*    slab = nullptr;  // one allocation holding everything below
+    float *  dx = nullptr, *dy = nullptr, *dz = nullptr;
+    float4*  pts = nullptr;
+    uint32_t* rank = nullptr;
+    uint32_t* hkeys = nullptr;
+    uint2*    hvals = nullptr;
+    b2::GridDev* grid = nullptr;
+    uint32_t* bbox_enc = nullptr;  // 6 order-encoded floats
+    uint32_t  hcap = 0, hshift = 0;
+    float     cell_req = 0;
+    cudaEvent_t ready = nullptr;
+
+    b2::CloudView view() const
+    {
+        b2::CloudView v;
+        v.pts = pts, v.rank = rank, v.grid = grid, v.hkeys = hkeys, v.hvals = hvals;
+        v.hshift = hshift, v.hmask = hcap - 1, v.n = (uint32_t)n;
+        return v;
+    }
+};
+
+namespace b2
+{
+// RAII lease of a workspace
+struct Lease
+{
+    ::b200icp* ctx;
+    Workspace* ws;
+    explicit Lease(::b200icp* c) : ctx(c), ws(c->acquire()) {}
+    ~Lease()
+    {
+        if (ws) ctx->release(ws);
+    }
+};
+
+int cloud_alloc(::b200icp* ctx, Workspace* ws, size_t n, float search_radius, b200icp_cloud** out);
+int cloud_build_index(::b200icp* ctx, Workspace* ws, b200icp_cloud* c);
+
+int run_align_batch(::b200icp* ctx, size_t n, const b200icp_cloud* const* from,
+                    const b200icp_cloud* const* to, const double* guesses, b200icp_result_t* out);
+int run_knn(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, const double* pose6,
+            uint32_t k, float max_dist, uint32_t* idx_out, float* d2_out);
+int run_match(::b200icp* ctx, const b200icp_cloud* from, const b200icp_cloud* to,
+              const double* pose6, uint8_t* paired, uint32_t* nn_idx, uint32_t* nn_cnt,
+              double* centroid, double* normal, uint32_t* n_pairings);
+int run_voxel(::b200icp* ctx, const b200icp_cloud* in, float resolution, int use_average,
+              float search_radius, b200icp_cloud** out, uint32_t* keep_idx);
+
+void make_dev_params(const b200icp_params_t& P, IcpDevParams& D);
+}  // namespace b2

@@ -1,0 +1,99 @@
+"""Whole registrations on the device vs the oracle (rows A, G-P): final pose
+within 1e-5 m / 1e-6 rad (BASELINE.json north_star), same iteration count,
+termination reason, pairing count and quality; covariance to 1e-6 relative."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_T, TOL_R = 1e-5, 1e-6
+
+
+def _assert_same(g, o, cov=True):
+    assert np.abs(g["pose"][:3] - o["pose"][:3]).max() < TOL_T, (g["pose"], o["pose"])
+    assert np.abs(g["pose"][3:] - o["pose"][3:]).max() < TOL_R, (g["pose"], o["pose"])
+    assert g["termination_reason"] == o["termination_reason"]
+    assert g["n_iterations"] == o["n_iterations"]
+    assert g["n_pairings"] == o["n_pairings"]
+    assert g["quality"] == o["quality"]
+    if cov and not o["cov_singular"]:
+        assert not g["cov_singular"]
+        scale = np.sqrt(np.outer(np.diag(o["cov"]), np.diag(o["cov"])))
+        assert np.abs(g["cov"] - o["cov"]).max() / scale.max() < 1e-5
+        assert (np.abs(g["cov"] - o["cov"]) / scale).max() < 1e-4
+
+
+def _run(icp, oracle, A, B, guess, params=None):
+    g_a, g_b = icp.upload(A), icp.upload(B)
+    g = icp.align(g_a, g_b, guess)
+    o = oracle.icp_align(oracle.Cloud(A), oracle.Cloud(B), guess,
+                         oracle.default_params() if params is None else params, kdtree=True)
+    g_a.free(), g_b.free()
+    return g, o
+
+
+@pytest.mark.parametrize("sigma", [0.0, 0.01])
+def test_c1_known_transform(icp, oracle, sigma):
+    """BASELINE config C1: two 20k-pt clouds, known rigid transform."""
+    from mola_fe_lidar_b200 import scene
+    A, B, pose = scene.make_pair_c1(seed=1, n=20000, sigma=sigma)
+    g, o = _run(icp, oracle, A, B, np.zeros(6))
+    _assert_same(g, o)
+    assert g["quality"] > 0.5
+
+
+def test_identity(icp, oracle):
+    from mola_fe_lidar_b200 import scene
+    A, _, _ = scene.make_pair_c1(seed=2, n=8000)
+    g, o = _run(icp, oracle, A, A, np.zeros(6))
+    _assert_same(g, o)
+    assert np.abs(g["pose"]).max() < 1e-9 and g["quality"] == 1.0
+    assert g["termination_reason"] == 4 and g["n_iterations"] <= 2
+
+
+def test_no_pairings(icp, oracle, rng):
+    A = rng.uniform(-5, 5, size=(2000, 3)).astype(np.float32)
+    B = A + np.float32(100.0)
+    g, o = _run(icp, oracle, A, B, np.zeros(6))
+    assert g["termination_reason"] == 1 == o["termination_reason"]
+    assert g["n_iterations"] == 0 and g["quality"] == 0.0 and g["cov_singular"] == 1
+    assert np.array_equal(g["pose"], o["pose"])
+
+
+def test_scan_to_scan_120k(icp, oracle):
+    """One step of BASELINE config C2 (raw 120k-pt scans)."""
+    from mola_fe_lidar_b200 import scene
+    scans, poses = scene.make_sequence(2, seed=1)
+    g, o = _run(icp, oracle, scans[0], scans[1], np.zeros(6))
+    _assert_same(g, o)
+
+
+def test_batch_equals_single(icp, oracle, rng):
+    """align_batch (Monte-Carlo guesses, LidarOdometry.cpp:775-787) == independent aligns."""
+    from mola_fe_lidar_b200 import scene
+    A, B, pose = scene.make_pair_c1(seed=3, n=6000, sigma=0.005)
+    C2, D2, _ = scene.make_pair_c1(seed=4, n=3000, sigma=0.0)
+    g_a, g_b, g_c, g_d = icp.upload(A), icp.upload(B), icp.upload(C2), icp.upload(D2)
+    guesses = pose + np.c_[rng.normal(0, 0.05, (5, 3)), rng.normal(0, 0.01, (5, 1)), np.zeros((5, 2))]
+    guesses = np.concatenate([guesses, np.zeros((1, 6))])
+    froms = [g_a] * 5 + [g_c]
+    tos = [g_b] * 5 + [g_d]
+    batch = icp.align_batch(froms, tos, guesses)
+    for i in range(6):
+        single = icp.align(froms[i], tos[i], guesses[i])
+        for key in ("pose", "cov"):
+            assert np.array_equal(batch[i][key], single[key]), key
+        for key in ("quality", "n_iterations", "termination_reason", "n_pairings"):
+            assert batch[i][key] == single[key], key
+    o = oracle.icp_align(oracle.Cloud(A), oracle.Cloud(B), guesses[0], oracle.default_params())
+    _assert_same(batch[0], o)
+
+
+def test_run_to_run_bit_reproducible(icp):
+    from mola_fe_lidar_b200 import scene
+    A, B, _ = scene.make_pair_c1(seed=5, n=10000, sigma=0.01)
+    g_a, g_b = icp.upload(A), icp.upload(B)
+    r1 = icp.align(g_a, g_b, np.zeros(6))
+    g_a2, g_b2 = icp.upload(A), icp.upload(B)
+    r2 = icp.align(g_a2, g_b2, np.zeros(6))
+    assert np.array_equal(r1["pose"], r2["pose"]) and np.array_equal(r1["cov"], r2["cov"])

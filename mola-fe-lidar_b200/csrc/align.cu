@@ -237,7 +237,10 @@ __global__ void __launch_bounds__(kChunk)
 
 // ------------------------------------------------------------------- solver
 // One CTA per job. Warp 0 runs the Gauss-Newton inner loop on the moments.
-__global__ void __launch_bounds__(128)
+constexpr int kSolveThreads = 640;
+constexpr int kSolveGroups = 8;  // 8 x 74 threads share the partials reduction
+
+__global__ void __launch_bounds__(kSolveThreads)
     solve_kernel(const CloudView* __restrict__ clouds, JobDev* __restrict__ jobs,
                  const double* __restrict__ partials, uint32_t max_chunks, IcpDevParams P,
                  uint32_t* __restrict__ n_active)
@@ -248,27 +251,36 @@ __global__ void __launch_bounds__(128)
     const int tid = threadIdx.x, lane = tid & 31;
 
     __shared__ double sM[kNumMoments];
+    __shared__ double sPart[kSolveGroups][kNumMoments];
     __shared__ double sA[144];
     __shared__ double sT0[12];   // theta0 layout: [R_i0 R_i1 R_i2 t_i] x 3
     __shared__ double sR[9], st[3];
     __shared__ double sX[12], sG12[12], sJ[72], sB[72], sH[36], sg[6];
     __shared__ int    sStop;
 
+    // fixed-order reduction of the per-CTA partials: group g takes the chunks
+    // c = g (mod 8) with two interleaved accumulators, then the 8 group sums
+    // are added as a balanced tree -- the order never depends on scheduling
     const uint32_t nchunks = (clouds[J.to_cloud].n + kChunk - 1) / kChunk;
+    if (tid < kSolveGroups * kNumMoments)
+    {
+        const int     grp = tid / kNumMoments, comp = tid % kNumMoments;
+        const double* p = partials + (size_t)job * max_chunks * kNumMoments + comp;
+        double        a0 = 0, a1 = 0;
+        uint32_t      c = grp;
+        for (; c + kSolveGroups < nchunks; c += 2 * kSolveGroups)
+        {
+            a0 += p[(size_t)c * kNumMoments];
+            a1 += p[(size_t)(c + kSolveGroups) * kNumMoments];
+        }
+        if (c < nchunks) a0 += p[(size_t)c * kNumMoments];
+        sPart[grp][comp] = a0 + a1;
+    }
+    __syncthreads();
     if (tid < kNumMoments)
     {
-        const double* p = partials + (size_t)job * max_chunks * kNumMoments + tid;
-        double        a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-        uint32_t      c = 0;
-        for (; c + 4 <= nchunks; c += 4)
-        {
-            a0 += p[(size_t)(c + 0) * kNumMoments];
-            a1 += p[(size_t)(c + 1) * kNumMoments];
-            a2 += p[(size_t)(c + 2) * kNumMoments];
-            a3 += p[(size_t)(c + 3) * kNumMoments];
-        }
-        for (; c < nchunks; c++) a0 += p[(size_t)c * kNumMoments];
-        const double s = (a0 + a1) + (a2 + a3);
+        const double s = ((sPart[0][tid] + sPart[1][tid]) + (sPart[2][tid] + sPart[3][tid])) +
+                         ((sPart[4][tid] + sPart[5][tid]) + (sPart[6][tid] + sPart[7][tid]));
         sM[tid] = s;
         J.M[tid] = s;
     }
@@ -705,7 +717,7 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
             launch_match<false>(ws, D.knn, mgrid, d_clouds, d_jobs, d_partials, max_chunks, D, no_out);
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 1], s));
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 2], s));
-            solve_kernel<<<(unsigned)n, 128, 0, s>>>(d_clouds, d_jobs, d_partials, max_chunks, D,
+            solve_kernel<<<(unsigned)n, kSolveThreads, 0, s>>>(d_clouds, d_jobs, d_partials, max_chunks, D,
                                                      d_active);
             ws->launches++;
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 3], s));

@@ -2,13 +2,18 @@
 //
 // Replaces the lazily built nanoflann kd-tree on the `from` cloud
 // (mrpt::math::KDTreeCapable) with a uniform grid:
-//   bbox -> per-point 30-bit Morton cell key -> radix sort (key, index) ->
-//   points gathered as float4 in cell order + inverse permutation ->
-//   open-addressing hash of occupied cells -> [start,end).
+//   bbox -> per-point key (30-bit Morton of the block | 6-bit fine cell) ->
+//   radix sort (key, index) -> points gathered as float4 in cell order +
+//   inverse permutation -> scan of fine-cell heads -> open-addressing hash of
+//   occupied blocks {start, first fine cell, 64-bit occupancy mask} and the
+//   start offset of every occupied fine cell.
 // Everything after the H2D copy happens on the device with no host sync.
 // Algorithmic traffic: 12 B read + 16 B float4 write + 4 B rank write per
 // point, plus the sort passes (36 B/point).
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
 
 #include "runtime.cuh"
 
@@ -81,7 +86,7 @@ __global__ void bbox_kernel(const float* __restrict__ x, const float* __restrict
     }
 }
 
-__global__ void grid_setup_kernel(const uint32_t* __restrict__ bb, float cell_req, GridDev* g)
+__global__ void grid_setup_kernel(const uint32_t* __restrict__ bb, float block_req, GridDev* g)
 {
     float mn[3], mx[3];
     for (int d = 0; d < 3; d++) mn[d] = dec_f(bb[d]), mx[d] = dec_f(bb[3 + d]);
@@ -89,94 +94,138 @@ __global__ void grid_setup_kernel(const uint32_t* __restrict__ bb, float cell_re
     if (!any)
         for (int d = 0; d < 3; d++) mn[d] = mx[d] = 0.f;
     float ext = fmaxf(fmaxf(mx[0] - mn[0], mx[1] - mn[1]), mx[2] - mn[2]);
-    // at most 1000 of the 1024 cells per axis may be spanned
-    const float cell = fmaxf(cell_req, ext / 1000.0f);
+    // at most 1000 of the 1024 blocks per axis may be spanned
+    const float block = fmaxf(block_req, ext / 1000.0f);
+    const float cell = block * 0.25f;
     g->ox = mn[0], g->oy = mn[1], g->oz = mn[2];
     g->cell = cell;
     g->inv_cell = 1.0f / cell;
-    g->slack = 6e-4f;  // > ulp(1024) = 1.2e-4 cells of rounding in (p - o) * inv_cell
+    g->slack = 2.5e-3f;  // > ulp(4096) = 4.9e-4 fine cells of rounding in (p - o) * inv_cell
     g->n_valid = 0;
     g->n_cells = 0;
+    g->n_blocks = 0;
     for (int d = 0; d < 3; d++) g->bmin[d] = mn[d], g->bmax[d] = mx[d];
 }
 
+constexpr unsigned long long kInvalidSortKey = 1ull << 36;
+
+// sort key = (Morton30 of the block) << 6 | fine cell inside the block
 __global__ void cell_key_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                 const float* __restrict__ z, uint32_t n,
-                                const GridDev* __restrict__ g, uint32_t* __restrict__ keys,
+                                const GridDev* __restrict__ g, unsigned long long* __restrict__ keys,
                                 uint32_t* __restrict__ vals)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float px = x[i], py = y[i], pz = z[i];
-    uint32_t key = 0xFFFFFFFFu;
+    const float        px = x[i], py = y[i], pz = z[i];
+    unsigned long long key = kInvalidSortKey;
     if (isfinite(px) && isfinite(py) && isfinite(pz))
     {
-        const float inv = g->inv_cell;
-        const int cx = min(max((int)floorf((px - g->ox) * inv), 0), kGridMax);
-        const int cy = min(max((int)floorf((py - g->oy) * inv), 0), kGridMax);
-        const int cz = min(max((int)floorf((pz - g->oz) * inv), 0), kGridMax);
-        key = spread10(cx) | (spread10(cy) << 1) | (spread10(cz) << 2);
+        const float    inv = g->inv_cell;
+        const uint32_t fx = (uint32_t)min(max((int)floorf((px - g->ox) * inv), 0), kFineMax);
+        const uint32_t fy = (uint32_t)min(max((int)floorf((py - g->oy) * inv), 0), kFineMax);
+        const uint32_t fz = (uint32_t)min(max((int)floorf((pz - g->oz) * inv), 0), kFineMax);
+        const uint32_t mort = spread10(fx >> 2) | (spread10(fy >> 2) << 1) | (spread10(fz >> 2) << 2);
+        const uint32_t sub = (fx & 3u) | ((fy & 3u) << 2) | ((fz & 3u) << 4);
+        key = ((unsigned long long)mort << 6) | sub;
     }
     keys[i] = key;
     vals[i] = i;
 }
 
 // After the sort: gather float4 points in cell order, write the inverse
-// permutation, and let the first point of every cell publish [start,end).
-__global__ void reorder_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ svals,
-                               uint32_t n, const float* __restrict__ x, const float* __restrict__ y,
-                               const float* __restrict__ z, float4* __restrict__ pts,
-                               uint32_t* __restrict__ rank, uint32_t* __restrict__ hkeys,
-                               uint2* __restrict__ hvals, uint32_t hshift, uint32_t hmask,
-                               GridDev* __restrict__ g)
+// permutation, flag the first point of every fine cell.
+__global__ void gather_kernel(const unsigned long long* __restrict__ skeys,
+                              const uint32_t* __restrict__ svals, uint32_t n,
+                              const float* __restrict__ x, const float* __restrict__ y,
+                              const float* __restrict__ z, float4* __restrict__ pts,
+                              uint32_t* __restrict__ rank, uint32_t* __restrict__ fine_flag,
+                              GridDev* __restrict__ g)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    const uint32_t key = skeys[j];
-    const uint32_t i = svals[j];
+    const unsigned long long key = skeys[j];
+    const uint32_t           i = svals[j];
     if (j == 0)
     {  // n_valid = first position holding the invalid key
         uint32_t lo = 0, hi = n;
         while (lo < hi)
         {
             const uint32_t mid = (lo + hi) >> 1;
-            if (skeys[mid] < 0xFFFFFFFFu)
+            if (skeys[mid] < kInvalidSortKey)
                 lo = mid + 1;
             else
                 hi = mid;
         }
         g->n_valid = lo;
     }
-    if (key == 0xFFFFFFFFu)
+    if (key >= kInvalidSortKey)
     {
         rank[i] = kInvalid;
+        fine_flag[j] = 0;
         return;
     }
     pts[j] = make_float4(x[i], y[i], z[i], __uint_as_float(i));
     rank[i] = j;
-    if (j == 0 || skeys[j - 1] != key)
+    fine_flag[j] = (j == 0 || skeys[j - 1] != key) ? 1u : 0u;
+}
+
+__device__ __forceinline__ uint32_t block_key_of(unsigned long long sort_key)
+{
+    const uint32_t mort = (uint32_t)(sort_key >> 6);
+    return compact10(mort) | (compact10(mort >> 1) << kGridBits) | (compact10(mort >> 2) << (2 * kGridBits));
+}
+
+// first point of every block claims a hash slot and writes its record
+__global__ void block_insert_kernel(const unsigned long long* __restrict__ skeys, uint32_t n,
+                                    const uint32_t* __restrict__ fine_flag,
+                                    const uint32_t* __restrict__ fine_ord,
+                                    uint32_t* __restrict__ hkeys, uint4* __restrict__ hrecs,
+                                    uint32_t hshift, uint32_t hmask, GridDev* __restrict__ g)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const unsigned long long key = skeys[j];
+    if (key >= kInvalidSortKey) return;
+    if (j != 0 && (skeys[j - 1] >> 6) == (key >> 6)) return;
+    const uint32_t bkey = block_key_of(key);
+    uint32_t       slot = hash_slot(bkey, hshift);
+    for (;;)
     {
-        uint32_t lo = j + 1, hi = n;  // upper bound of this key
-        while (lo < hi)
-        {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (skeys[mid] <= key)
-                lo = mid + 1;
-            else
-                hi = mid;
-        }
-        const uint32_t ckey = compact10(key) | (compact10(key >> 1) << kGridBits) |
-                              (compact10(key >> 2) << (2 * kGridBits));
-        uint32_t slot = hash_slot(ckey, hshift);
-        for (;;)
-        {
-            const uint32_t prev = atomicCAS(hkeys + slot, kEmptyKey, ckey);
-            if (prev == kEmptyKey) break;
-            slot = (slot + 1) & hmask;
-        }
-        hvals[slot] = make_uint2(j, lo);
-        atomicAdd(&g->n_cells, 1u);
+        const uint32_t prev = atomicCAS(hkeys + slot, kEmptyKey, bkey);
+        if (prev == kEmptyKey) break;
+        slot = (slot + 1) & hmask;
     }
+    hrecs[slot] = make_uint4(j, fine_ord[j], 0u, 0u);
+    atomicAdd(&g->n_blocks, 1u);
+}
+
+// first point of every fine cell publishes its start and sets its mask bit
+__global__ void fine_publish_kernel(const unsigned long long* __restrict__ skeys, uint32_t n,
+                                    const uint32_t* __restrict__ fine_flag,
+                                    const uint32_t* __restrict__ fine_ord,
+                                    const uint32_t* __restrict__ hkeys, uint4* __restrict__ hrecs,
+                                    uint32_t hshift, uint32_t hmask,
+                                    uint32_t* __restrict__ fine_start, GridDev* __restrict__ g)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const unsigned long long key = skeys[j];
+    if (key >= kInvalidSortKey) return;
+    const bool last = (j + 1 == n) || (skeys[j + 1] >= kInvalidSortKey);
+    if (last)
+    {
+        const uint32_t total = fine_ord[j] + fine_flag[j];
+        fine_start[total] = j + 1;
+        g->n_cells = total;
+    }
+    if (!fine_flag[j]) return;
+    fine_start[fine_ord[j]] = j;
+    const uint32_t bkey = block_key_of(key);
+    uint32_t       slot = hash_slot(bkey, hshift);
+    while (hkeys[slot] != bkey) slot = (slot + 1) & hmask;
+    unsigned long long* mask = reinterpret_cast<unsigned long long*>(&hrecs[slot].z);
+    atomicOr(mask, 1ull << (uint32_t)(key & 63ull));
 }
 
 int cloud_alloc(::b200icp* ctx, Workspace* ws, size_t n, float search_radius, b200icp_cloud** out)
@@ -205,7 +254,8 @@ int cloud_alloc(::b200icp* ctx, Workspace* ws, size_t n, float search_radius, b2
         c->pts = k.take<float4>(nn);
         c->rank = k.take<uint32_t>(nn);
         c->hkeys = k.take<uint32_t>(cap);
-        c->hvals = k.take<uint2>(cap);
+        c->hrecs = k.take<uint4>(cap);
+        c->fine_start = k.take<uint32_t>(nn + 1);
         c->grid = k.take<GridDev>(1);
         c->bbox_enc = k.take<uint32_t>(8);
     };
@@ -255,29 +305,40 @@ int cloud_build_index(::b200icp* ctx, Workspace* ws, b200icp_cloud* c)
     ws->launches++;
     if (n)
     {
-        size_t temp_bytes = 0;
-        cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr), dv(nullptr, nullptr);
-        B2_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, dk, dv, (int)n, 0, 32, s));
+        size_t sort_bytes = 0, scan_bytes = 0;
+        cub::DoubleBuffer<unsigned long long> dk(nullptr, nullptr);
+        cub::DoubleBuffer<uint32_t>           dv(nullptr, nullptr);
+        B2_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, dk, dv, (int)n, 0, 37, s));
+        B2_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (uint32_t*)nullptr,
+                                                  (uint32_t*)nullptr, (int)n, s));
+        const size_t temp_bytes = std::max(sort_bytes, scan_bytes);
+        unsigned long long *k0, *k1;
+        uint32_t *          v0, *v1, *fflag, *ford;
+        void*               temp;
+        auto layout = [&](Carver& k) {
+            k0 = k.take<unsigned long long>(n), k1 = k.take<unsigned long long>(n);
+            v0 = k.take<uint32_t>(n), v1 = k.take<uint32_t>(n);
+            fflag = k.take<uint32_t>(n), ford = k.take<uint32_t>(n);
+            temp = k.take<char>(temp_bytes);
+        };
         Carver cv(nullptr);
-        cv.take<uint32_t>(n), cv.take<uint32_t>(n), cv.take<uint32_t>(n), cv.take<uint32_t>(n);
-        cv.take<char>(temp_bytes);
+        layout(cv);
         if (int r = ws->reserve_device(cv.off)) return r;
-        Carver   k(ws->d_scratch);
-        uint32_t* k0 = k.take<uint32_t>(n);
-        uint32_t* k1 = k.take<uint32_t>(n);
-        uint32_t* v0 = k.take<uint32_t>(n);
-        uint32_t* v1 = k.take<uint32_t>(n);
-        void*     temp = k.take<char>(temp_bytes);
+        Carver k(ws->d_scratch);
+        layout(k);
         const int blocks = (int)((n + 255) / 256);
         cell_key_kernel<<<blocks, 256, 0, s>>>(c->dx, c->dy, c->dz, n, c->grid, k0, v0);
-        ws->launches++;
-        cub::DoubleBuffer<uint32_t> keys(k0, k1), vals(v0, v1);
-        B2_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, vals, (int)n, 0, 32, s));
-        ws->launches += 5;  // upsweep/scan/downsweep passes (onesweep: histogram + 4 passes)
-        reorder_kernel<<<blocks, 256, 0, s>>>(keys.Current(), vals.Current(), n, c->dx, c->dy,
-                                              c->dz, c->pts, c->rank, c->hkeys, c->hvals,
-                                              c->hshift, c->hcap - 1, c->grid);
-        ws->launches++;
+        cub::DoubleBuffer<unsigned long long> keys(k0, k1);
+        cub::DoubleBuffer<uint32_t>           vals(v0, v1);
+        B2_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, sort_bytes, keys, vals, (int)n, 0, 37, s));
+        gather_kernel<<<blocks, 256, 0, s>>>(keys.Current(), vals.Current(), n, c->dx, c->dy, c->dz,
+                                             c->pts, c->rank, fflag, c->grid);
+        B2_CUDA_TRY(cub::DeviceScan::ExclusiveSum(temp, scan_bytes, fflag, ford, (int)n, s));
+        block_insert_kernel<<<blocks, 256, 0, s>>>(keys.Current(), n, fflag, ford, c->hkeys, c->hrecs,
+                                                   c->hshift, c->hcap - 1, c->grid);
+        fine_publish_kernel<<<blocks, 256, 0, s>>>(keys.Current(), n, fflag, ford, c->hkeys, c->hrecs,
+                                                   c->hshift, c->hcap - 1, c->fine_start, c->grid);
+        ws->launches += 4 + 6 + 2;  // ours + radix sort passes + scan
     }
     B2_CUDA_TRY(cudaGetLastError());
     B2_CUDA_TRY(cudaEventRecord(c->ready, s));

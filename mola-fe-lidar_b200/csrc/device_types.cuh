@@ -3,12 +3,19 @@
 // A cloud (one point layer of the reference's mp2p_icp::metric_map_t, i.e. MRPT
 // CPointsMap SoA float buffers -- SURVEY.md Appendix A.1) lives in HBM as:
 //   x[n], y[n], z[n]      original order (what the caller uploaded)
-//   pts[n_valid] float4   (x, y, z, bitcast original index), sorted by the
-//                         30-bit Morton code of the point's grid cell
+//   pts[n_valid] float4   (x, y, z, bitcast original index), sorted by
+//                         (30-bit Morton code of the point's BLOCK, 6-bit fine
+//                         cell inside the block)
 //   rank[n]               original index -> sorted position
-//   hkeys/hvals           open-addressing hash: linear cell key -> [start,end)
+//   hkeys/hrecs           open-addressing hash: linear block key -> BlockRec
+//                         {first point, first fine-cell ordinal, 64-bit
+//                         occupancy mask of its 4x4x4 fine cells}
+//   fine_start[n_fine+1]  first point of every occupied fine cell, in order
 //   GridDev               grid origin / cell size / counts, written on device
-// The uniform grid replaces the lazily built nanoflann kd-tree (row I).
+// Two levels: a BLOCK (edge >= the search radius, so 27 blocks always cover
+// the radius) holds 4x4x4 FINE cells; dense regions are pruned at fine-cell
+// granularity while empty space costs one hash probe per block.
+// The grid replaces the lazily built nanoflann kd-tree (row I).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -17,21 +24,23 @@ namespace b2
 {
 constexpr uint32_t kInvalid = 0xFFFFFFFFu;
 constexpr uint32_t kEmptyKey = 0xFFFFFFFFu;
-constexpr int kGridBits = 10;  // cells per axis = 1024 (30-bit Morton / linear keys)
+constexpr int kGridBits = 10;  // blocks per axis = 1024 (30-bit Morton / linear keys)
 constexpr int kGridMax = (1 << kGridBits) - 1;
+constexpr int kFineMax = 4 * (kGridMax + 1) - 1;  // fine cells per axis - 1
 constexpr int kChunk = 128;    // queries per CTA in the matcher kernels
 constexpr int kNumMoments = 74; // 60 (nn x hh) + 12 (r0 n x h) + 1 (r0^2) + 1 (count)
 
 struct GridDev
 {
     float    ox, oy, oz;  // origin = bbox min of the finite points
-    float    cell;        // cell edge actually used (>= requested)
+    float    cell;        // FINE cell edge actually used (block edge = 4 * cell)
     float    inv_cell;
     float    slack;       // in cell units: guards float rounding in cell assignment
     uint32_t n_valid;     // finite points (sorted first)
-    uint32_t n_cells;     // occupied cells
+    uint32_t n_cells;     // occupied fine cells
+    uint32_t n_blocks;    // occupied blocks
     float    bmin[3], bmax[3];
-    uint32_t pad[2];
+    uint32_t pad[1];
 };
 
 struct CloudView
@@ -40,7 +49,8 @@ struct CloudView
     const uint32_t* rank;
     const GridDev*  grid;
     const uint32_t* hkeys;
-    const uint2*    hvals;
+    const uint4*    hrecs;       // BlockRec as (start, fine_base, mask.lo, mask.hi)
+    const uint32_t* fine_start;
     uint32_t        hshift;  // 32 - log2(capacity)
     uint32_t        hmask;   // capacity - 1
     uint32_t        n;       // total points (incl. non-finite)

@@ -1,15 +1,18 @@
 // knn_search.cuh -- radius-capped exact k-nearest-neighbour search on the
-// uniform-grid / cell-hash index (replaces kdTreeNClosestPoint3DIdx on the
-// nanoflann kd-tree behind mp2p_icp's matchers).
+// two-level grid index (replaces kdTreeNClosestPoint3DIdx on the nanoflann
+// kd-tree behind mp2p_icp's matchers).
 //
 // Result = the k smallest (d2 as float32, original index) keys with
 // d2 <= cap_d2, ascending -- the tie rule of Appendix A.4. d2 is evaluated
 // in the fixed float order of A.3 (the library is built with -fmad=false).
 //
-// One thread per query. Cells are visited nearest-first (zig-zag over the
-// offsets of each axis) and a cell / row / slab is skipped as soon as its
-// minimum possible distance exceeds the current k-th best, so in dense regions
-// only the query's own cell and the few cells it nearly touches are scanned.
+// One thread per query. Fine cells are visited in SHELLS of growing Chebyshev
+// distance from the query's own fine cell (nearest first); the search stops
+// as soon as the next shell cannot hold anything closer than the current k-th
+// best. Per shell only the (<= 27) blocks the shell touches are probed in the
+// hash, each yields a 64-bit occupancy mask, and the shell's surface inside
+// the block is one AND with three precomputed bit patterns -- empty space
+// costs one probe per block, dense regions are pruned per fine cell.
 #pragma once
 #include "device_types.cuh"
 
@@ -25,8 +28,6 @@ __device__ __forceinline__ uint64_t sentinel_key(float cap_d2)
 }
 __device__ __forceinline__ float key_d2(uint64_t k) { return __uint_as_float((uint32_t)(k >> 32)); }
 __device__ __forceinline__ uint32_t key_idx(uint64_t k) { return (uint32_t)(k & 0xFFFFFFFFull); }
-
-__device__ __forceinline__ int zig(int s) { return (s & 1) ? -((s + 1) >> 1) : (s >> 1); }
 
 // distance (in cell units) from a point with fractional in-cell position f to
 // the cell `d` cells away along one axis, made conservative by `slack`
@@ -56,16 +57,82 @@ __device__ __forceinline__ void topk_insert(uint64_t (&key)[K], uint64_t kk)
     }
 }
 
-// Looks the linear cell key up; returns [start,end) or an empty range.
-__device__ __forceinline__ uint2 cell_lookup(const CloudView& cv, uint32_t ckey)
+// 4-bit pattern of the in-block sub indices inside [lo,hi] (0 when empty)
+__device__ __forceinline__ uint32_t range4(int lo, int hi)
 {
-    uint32_t slot = hash_slot(ckey, cv.hshift);
+    lo = max(lo, 0);
+    hi = min(hi, 3);
+    return (lo > hi) ? 0u : ((2u << hi) - (1u << lo));
+}
+// fine cell (sx,sy,sz) of a block is bit sx + 4*sy + 16*sz of its mask
+__device__ __forceinline__ uint64_t expand_x(uint32_t p) { return (uint64_t)p * 0x1111111111111111ull; }
+__device__ __forceinline__ uint64_t expand_y(uint32_t p)
+{
+    const uint32_t n = ((p & 1u) * 0xFu) | ((p & 2u) * 0x78u) | ((p & 4u) * 0x3C0u) | ((p & 8u) * 0x1E00u);
+    return (uint64_t)n * 0x0001000100010001ull;
+}
+__device__ __forceinline__ uint64_t expand_z(uint32_t p)
+{
+    return ((p & 1u) ? 0xFFFFull : 0ull) | ((p & 2u) ? 0xFFFF0000ull : 0ull) |
+           ((p & 4u) ? 0xFFFF00000000ull : 0ull) | ((p & 8u) ? 0xFFFF000000000000ull : 0ull);
+}
+
+__device__ __forceinline__ bool block_lookup(const CloudView& cv, uint32_t bkey, uint4& rec)
+{
+    uint32_t slot = hash_slot(bkey, cv.hshift);
     for (;;)
     {
         const uint32_t k = __ldg(cv.hkeys + slot);
-        if (k == ckey) return __ldg(cv.hvals + slot);
-        if (k == kEmptyKey) return make_uint2(0u, 0u);
+        if (k == bkey)
+        {
+            rec = __ldg(cv.hrecs + slot);
+            return true;
+        }
+        if (k == kEmptyKey) return false;
         slot = (slot + 1) & cv.hmask;
+    }
+}
+
+__device__ __forceinline__ float dist2(float qx, float qy, float qz, const float4& c)
+{
+    const float ddx = qx - c.x, ddy = qy - c.y, ddz = qz - c.z;
+    const float a = ddx * ddx;
+    const float b = ddy * ddy;
+    const float e = ddz * ddz;
+    const float ab = a + b;
+    return ab + e;  // A.3: ((dx^2 + dy^2) + dz^2), no contraction
+}
+
+// all points of one fine cell, [beg,end) in the sorted array
+template <int K>
+__device__ __forceinline__ void scan_range(const float4* __restrict__ pts, uint32_t beg,
+                                           uint32_t end, float qx, float qy, float qz,
+                                           uint64_t (&key)[K])
+{
+    uint32_t j = beg;
+    for (; j + 4 <= end; j += 4)
+    {
+        // four independent loads in flight before the first use
+        const float4   c0 = __ldg(pts + j), c1 = __ldg(pts + j + 1), c2 = __ldg(pts + j + 2),
+                     c3 = __ldg(pts + j + 3);
+        const uint64_t k0 = make_key(dist2(qx, qy, qz, c0), __float_as_uint(c0.w));
+        const uint64_t k1 = make_key(dist2(qx, qy, qz, c1), __float_as_uint(c1.w));
+        const uint64_t k2 = make_key(dist2(qx, qy, qz, c2), __float_as_uint(c2.w));
+        const uint64_t k3 = make_key(dist2(qx, qy, qz, c3), __float_as_uint(c3.w));
+        const uint64_t w = key[K - 1];
+        if (k0 < w || k1 < w || k2 < w || k3 < w)
+        {
+            if (k0 < key[K - 1]) topk_insert<K>(key, k0);
+            if (k1 < key[K - 1]) topk_insert<K>(key, k1);
+            if (k2 < key[K - 1]) topk_insert<K>(key, k2);
+            if (k3 < key[K - 1]) topk_insert<K>(key, k3);
+        }
+    }
+    for (; j < end; j++)
+    {
+        const float4   c = __ldg(pts + j);
+        const uint64_t kk = make_key(dist2(qx, qy, qz, c), __float_as_uint(c.w));
+        if (kk < key[K - 1]) topk_insert<K>(key, kk);
     }
 }
 
@@ -75,64 +142,74 @@ __device__ __forceinline__ void knn_search(const CloudView& cv, const GridDev& g
                                            float qy, float qz, float cap_d2,
                                            uint64_t (&key)[K])
 {
-    // rings of cells that can hold a point within the cap
-    const float cap = sqrtf(cap_d2);
-    const int   R = max(1, (int)ceilf(cap * g.inv_cell * 1.0005f));
-    const float lim_lo = -(float)(R + 2), lim_hi = (float)(kGridMax + R + 3);
-    float ux = (qx - g.ox) * g.inv_cell, uy = (qy - g.oy) * g.inv_cell,
-          uz = (qz - g.oz) * g.inv_cell;
+    const float inv = g.inv_cell;
+    // shells of fine cells that can hold a point within the cap
+    const int   S = max(1, (int)ceilf(sqrtf(cap_d2) * inv * 1.0005f));
+    const float lim_lo = -(float)(S + 2), lim_hi = (float)(kFineMax + S + 3);
+    float       ux = (qx - g.ox) * inv, uy = (qy - g.oy) * inv, uz = (qz - g.oz) * inv;
     if (!(ux == ux) || !(uy == uy) || !(uz == uz)) return;  // NaN query: no neighbours
     ux = fminf(fmaxf(ux, lim_lo), lim_hi);
     uy = fminf(fmaxf(uy, lim_lo), lim_hi);
     uz = fminf(fmaxf(uz, lim_lo), lim_hi);
     const float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
-    const int   cqx = (int)flx, cqy = (int)fly, cqz = (int)flz;
+    const int   qfx = (int)flx, qfy = (int)fly, qfz = (int)flz;
     const float fx = ux - flx, fy = uy - fly, fz = uz - flz;
     const float slack = g.slack;
-    // worst admissible d2 in cell units, with a relative guard for rounding
-    const float to_cells2 = g.inv_cell * g.inv_cell;
-    float worst = key_d2(key[K - 1]) * to_cells2 * 1.0001f;
+    // distance from the query to the nearest face of its own fine cell
+    const float gmin = fmaxf(
+        fminf(fminf(fminf(fx, 1.0f - fx), fminf(fy, 1.0f - fy)), fminf(fz, 1.0f - fz)) - slack, 0.0f);
+    // worst admissible d2 in fine-cell units, with a relative guard for rounding
+    const float to_cells2 = inv * inv * 1.0001f;
+    float       worst = key_d2(key[K - 1]) * to_cells2;
 
-    for (int sz = 0; sz <= 2 * R; sz++)
+    for (int s = 0; s <= S; s++)
     {
-        const int dz = zig(sz);
-        const int cz = cqz + dz;
-        if (cz < 0 || cz > kGridMax) continue;
-        const float gz = axis_gap(fz, dz, slack);
-        const float gz2 = gz * gz;
-        if (gz2 > worst) continue;
-        for (int sy = 0; sy <= 2 * R; sy++)
+        if (s >= 1)
+        {  // every cell of shell s is at least (s - 1 + gmin) cells away
+            const float b = (float)(s - 1) + gmin;
+            if (b * b > worst) break;
+        }
+        const int x0 = qfx - s, x1 = qfx + s, y0 = qfy - s, y1 = qfy + s, z0 = qfz - s, z1 = qfz + s;
+        const int bx0 = max(x0 >> 2, 0), bx1 = min(x1 >> 2, kGridMax);
+        const int by0 = max(y0 >> 2, 0), by1 = min(y1 >> 2, kGridMax);
+        const int bz0 = max(z0 >> 2, 0), bz1 = min(z1 >> 2, kGridMax);
+        for (int bz = bz0; bz <= bz1; bz++)
         {
-            const int dy = zig(sy);
-            const int cy = cqy + dy;
-            if (cy < 0 || cy > kGridMax) continue;
-            const float gy = axis_gap(fy, dy, slack);
-            const float gzy2 = gz2 + gy * gy;
-            if (gzy2 > worst) continue;
-            for (int sx = 0; sx <= 2 * R; sx++)
+            const uint64_t Zs = expand_z(range4(z0 - 4 * bz, z1 - 4 * bz));
+            const uint64_t Zi = expand_z(s ? range4(z0 + 1 - 4 * bz, z1 - 1 - 4 * bz) : 0u);
+            for (int by = by0; by <= by1; by++)
             {
-                const int dx = zig(sx);
-                const int cx = cqx + dx;
-                if (cx < 0 || cx > kGridMax) continue;
-                const float gx = axis_gap(fx, dx, slack);
-                if (gzy2 + gx * gx > worst) continue;
-                const uint32_t ckey =
-                    (uint32_t)cx | ((uint32_t)cy << kGridBits) | ((uint32_t)cz << (2 * kGridBits));
-                const uint2 range = cell_lookup(cv, ckey);
-                for (uint32_t j = range.x; j < range.y; j++)
+                const uint64_t Ys = expand_y(range4(y0 - 4 * by, y1 - 4 * by));
+                const uint64_t Yi = expand_y(s ? range4(y0 + 1 - 4 * by, y1 - 1 - 4 * by) : 0u);
+                const uint64_t ZYs = Zs & Ys, ZYi = Zi & Yi;
+                for (int bx = bx0; bx <= bx1; bx++)
                 {
-                    const float4 c = __ldg(cv.pts + j);
-                    const float  ddx = qx - c.x, ddy = qy - c.y, ddz = qz - c.z;
-                    const float  a = ddx * ddx;
-                    const float  b = ddy * ddy;
-                    const float  e = ddz * ddz;
-                    const float  ab = a + b;
-                    const float  d2 = ab + e;
-                    const uint64_t kk = make_key(d2, __float_as_uint(c.w));
-                    if (kk < key[K - 1])
+                    const uint64_t Xs = expand_x(range4(x0 - 4 * bx, x1 - 4 * bx));
+                    const uint64_t Xi = expand_x(s ? range4(x0 + 1 - 4 * bx, x1 - 1 - 4 * bx) : 0u);
+                    // surface of the shell's cube inside this block
+                    uint64_t m = (ZYs & Xs) & ~(ZYi & Xi);
+                    if (m == 0) continue;
+                    uint4 rec;
+                    const uint32_t bkey = (uint32_t)bx | ((uint32_t)by << kGridBits) |
+                                          ((uint32_t)bz << (2 * kGridBits));
+                    if (!block_lookup(cv, bkey, rec)) continue;
+                    const uint64_t occ = ((uint64_t)rec.w << 32) | (uint64_t)rec.z;
+                    m &= occ;
+                    while (m)
                     {
-                        topk_insert<K>(key, kk);
-                        worst = key_d2(key[K - 1]) * to_cells2 * 1.0001f;
+                        const int bit = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        const int   cx = 4 * bx + (bit & 3), cy = 4 * by + ((bit >> 2) & 3),
+                                  cz = 4 * bz + (bit >> 4);
+                        const float gx = axis_gap(fx, cx - qfx, slack);
+                        const float gy = axis_gap(fy, cy - qfy, slack);
+                        const float gz = axis_gap(fz, cz - qfz, slack);
+                        if ((gx * gx + gy * gy) + gz * gz > worst) continue;
+                        const uint32_t ord = rec.y + (uint32_t)__popcll(occ & ((1ull << bit) - 1ull));
+                        const uint32_t beg = __ldg(cv.fine_start + ord);
+                        const uint32_t end = __ldg(cv.fine_start + ord + 1);
+                        scan_range<K>(cv.pts, beg, end, qx, qy, qz, key);
+                        worst = key_d2(key[K - 1]) * to_cells2;
                     }
                 }
             }

@@ -94,7 +94,8 @@ struct b200icp_cloud
     float4*  pts = nullptr;
     uint32_t* rank = nullptr;
     uint32_t* hkeys = nullptr;
-    uint2*    hvals = nullptr;
+    uint4*    hrecs = nullptr;
+    uint32_t* fine_start = nullptr;
     b2::GridDev* grid = nullptr;
     uint32_t* bbox_enc = nullptr;  // 6 order-encoded floats
     uint32_t  hcap = 0, hshift = 0;
@@ -104,7 +105,8 @@ struct b200icp_cloud
     b2::CloudView view() const
     {
         b2::CloudView v;
-        v.pts = pts, v.rank = rank, v.grid = grid, v.hkeys = hkeys, v.hvals = hvals;
+        v.pts = pts, v.rank = rank, v.grid = grid, v.hkeys = hkeys, v.hrecs = hrecs;
+        v.fine_start = fine_start;
         v.hshift = hshift, v.hmask = hcap - 1, v.n = (uint32_t)n;
         return v;
     }

@@ -20,6 +20,8 @@
 // perturbation T (+) exp(eps).  One pass over the pairings per OUTER iteration
 // instead of one per inner iteration; the iterates equal the reference's
 // per-pairing Gauss-Newton in exact arithmetic.
+#include <cub/device/device_radix_sort.cuh>
+
 #include "icp_math.cuh"
 #include "knn_search.cuh"
 #include "runtime.cuh"
@@ -70,6 +72,7 @@ struct MatchOut
 template <int K, bool WRITE>
 __global__ void __launch_bounds__(kChunk)
     match_kernel(const CloudView* __restrict__ clouds, const JobDev* __restrict__ jobs,
+                 const uint32_t* __restrict__ qorder, const uint32_t* __restrict__ qoff,
                  double* __restrict__ partials, uint32_t max_chunks, IcpDevParams P, MatchOut out)
 {
     const uint32_t job = blockIdx.y;
@@ -93,7 +96,10 @@ __global__ void __launch_bounds__(kChunk)
     const uint32_t it = J.iter;
     const bool     active = (P.run_from_iteration <= it) &&
                         (P.run_up_to_iteration == 0 || it <= P.run_up_to_iteration);
-    const uint32_t qi = blockIdx.x * kChunk + tid;
+    // queries are taken in the order of their bin (global fine cell under a
+    // recent pose): the lanes of a warp then walk the same shells / blocks
+    const uint32_t slot = blockIdx.x * kChunk + tid;
+    const uint32_t qi = (slot < cvL.n) ? __ldg(qorder + qoff[job] + slot) : kInvalid;
     const bool     valid = active && (qi < s_nvalid) && (sgrid.n_valid > 0);
 
     bool   paired = false;
@@ -266,15 +272,25 @@ __global__ void __launch_bounds__(kSolveThreads)
     {
         const int     grp = tid / kNumMoments, comp = tid % kNumMoments;
         const double* p = partials + (size_t)job * max_chunks * kNumMoments + comp;
-        double        a0 = 0, a1 = 0;
+        double        a0 = 0, a1 = 0, a2 = 0, a3 = 0;
         uint32_t      c = grp;
-        for (; c + kSolveGroups < nchunks; c += 2 * kSolveGroups)
+        // eight loads in flight per thread: the partials sit in L2, the loop
+        // is latency bound
+        for (; c + 7 * kSolveGroups < nchunks; c += 8 * kSolveGroups)
         {
-            a0 += p[(size_t)c * kNumMoments];
-            a1 += p[(size_t)(c + kSolveGroups) * kNumMoments];
+            const double v0 = p[(size_t)c * kNumMoments];
+            const double v1 = p[(size_t)(c + kSolveGroups) * kNumMoments];
+            const double v2 = p[(size_t)(c + 2 * kSolveGroups) * kNumMoments];
+            const double v3 = p[(size_t)(c + 3 * kSolveGroups) * kNumMoments];
+            const double v4 = p[(size_t)(c + 4 * kSolveGroups) * kNumMoments];
+            const double v5 = p[(size_t)(c + 5 * kSolveGroups) * kNumMoments];
+            const double v6 = p[(size_t)(c + 6 * kSolveGroups) * kNumMoments];
+            const double v7 = p[(size_t)(c + 7 * kSolveGroups) * kNumMoments];
+            a0 += v0, a1 += v1, a2 += v2, a3 += v3;
+            a0 += v4, a1 += v5, a2 += v6, a3 += v7;
         }
-        if (c < nchunks) a0 += p[(size_t)c * kNumMoments];
-        sPart[grp][comp] = a0 + a1;
+        for (; c < nchunks; c += kSolveGroups) a0 += p[(size_t)c * kNumMoments];
+        sPart[grp][comp] = (a0 + a1) + (a2 + a3);
     }
     __syncthreads();
     if (tid < kNumMoments)
@@ -386,7 +402,7 @@ __global__ void __launch_bounds__(kSolveThreads)
             double Hm[36], mg[6], delta[6];
             for (int i = 0; i < 36; i++) Hm[i] = 0.5 * (sH[i] + sH[(i % 6) * 6 + i / 6]);
             for (int i = 0; i < 6; i++) mg[i] = -sg[i];
-            qr_solve6(Hm, mg, delta);
+            solve6_spd(Hm, mg, delta);
             Pose T, dT, Tn;
             for (int i = 0; i < 9; i++) T.R[i] = sR[i];
             for (int i = 0; i < 3; i++) T.t[i] = st[i];
@@ -440,7 +456,9 @@ __global__ void __launch_bounds__(kSolveThreads)
 // ------------------------------------------------------------------ quality
 // QualityEvaluator_PairedRatio (row O / A.8): 1-NN within thresholdDistance.
 __global__ void __launch_bounds__(kChunk)
-    quality_kernel(const CloudView* __restrict__ clouds, JobDev* __restrict__ jobs, IcpDevParams P)
+    quality_kernel(const CloudView* __restrict__ clouds, JobDev* __restrict__ jobs,
+                   const uint32_t* __restrict__ qorder, const uint32_t* __restrict__ qoff,
+                   IcpDevParams P)
 {
     const uint32_t  job = blockIdx.y;
     JobDev&         J = jobs[job];
@@ -456,7 +474,8 @@ __global__ void __launch_bounds__(kChunk)
     if (tid == 32) sgrid = *cvG.grid;
     if (tid == 64) s_nvalid = cvL.grid->n_valid;
     __syncthreads();
-    const uint32_t qi = blockIdx.x * kChunk + tid;
+    const uint32_t slot = blockIdx.x * kChunk + tid;
+    const uint32_t qi = (slot < cvL.n) ? __ldg(qorder + qoff[job] + slot) : kInvalid;
     bool           hit = false;
     if (qi < s_nvalid && sgrid.n_valid > 0)
     {
@@ -531,7 +550,7 @@ __global__ void __launch_bounds__(64) covariance_kernel(JobDev* __restrict__ job
     {
         double Hm[36], Ci[36];
         for (int i = 0; i < 36; i++) Hm[i] = 0.5 * (sH[i] + sH[(i % 6) * 6 + i / 6]);
-        const int rank = inverse6(Hm, Ci);
+        const int rank = inverse6_spd(Hm, Ci);
         for (int i = 0; i < 36; i++) J.cov[i] = (rank == 6) ? Ci[i] : 0.0;
         J.cov_singular = (rank == 6) ? 0u : 1u;
     }
@@ -540,15 +559,18 @@ __global__ void __launch_bounds__(64) covariance_kernel(JobDev* __restrict__ job
 // ---------------------------------------------------------------- kNN query
 template <int K>
 __global__ void __launch_bounds__(kChunk)
-    knn_kernel(CloudView cvG, CloudView cvL, Pose T, uint32_t k, float cap_d2,
-               uint32_t* __restrict__ idx_out, float* __restrict__ d2_out)
+    knn_kernel(CloudView cvG, CloudView cvL, const uint32_t* __restrict__ qorder, Pose T,
+               uint32_t k, float cap_d2, uint32_t* __restrict__ idx_out,
+               float* __restrict__ d2_out)
 {
     __shared__ GridDev sgrid;
     __shared__ uint32_t s_nvalid;
     if (threadIdx.x == 0) sgrid = *cvG.grid;
     if (threadIdx.x == 32) s_nvalid = cvL.grid->n_valid;
     __syncthreads();
-    const uint32_t qi = blockIdx.x * kChunk + threadIdx.x;
+    const uint32_t slot = blockIdx.x * kChunk + threadIdx.x;
+    if (slot >= cvL.n) return;
+    const uint32_t qi = __ldg(qorder + slot);
     if (qi >= s_nvalid) return;
     const float4 pl = __ldg(cvL.pts + qi);
     const double px = pl.x, py = pl.y, pz = pl.z;
@@ -571,6 +593,42 @@ __global__ void __launch_bounds__(kChunk)
         }
 }
 
+// ------------------------------------------------------------- query binning
+// Key of every query of every job = (job, sort key of the GLOBAL fine cell its
+// transformed position falls in). Sorting these pairs makes the lanes of a
+// warp share home cells, hence shells, blocks and candidate ranges. The order
+// only affects which lanes work together and the (fixed) summation order.
+__global__ void __launch_bounds__(kChunk)
+    bin_key_kernel(const CloudView* __restrict__ clouds, const JobDev* __restrict__ jobs,
+                   const uint32_t* __restrict__ qoff, unsigned long long* __restrict__ keys,
+                   uint32_t* __restrict__ vals)
+{
+    const uint32_t  job = blockIdx.y;
+    const JobDev&   J = jobs[job];
+    const CloudView cvL = clouds[J.to_cloud];
+    const uint32_t  slot = blockIdx.x * kChunk + threadIdx.x;
+    if (slot >= cvL.n) return;
+    const GridDev* g = clouds[J.from_cloud].grid;
+    unsigned long long key = kInvalidSortKey;
+    if (slot < cvL.grid->n_valid)
+    {
+        const float4 pl = __ldg(cvL.pts + slot);
+        const double px = pl.x, py = pl.y, pz = pl.z;
+        const float  qx = (float)(((J.R[0] * px + J.R[1] * py) + J.R[2] * pz) + J.t[0]);
+        const float  qy = (float)(((J.R[3] * px + J.R[4] * py) + J.R[5] * pz) + J.t[1]);
+        const float  qz = (float)(((J.R[6] * px + J.R[7] * py) + J.R[8] * pz) + J.t[2]);
+        const float  inv = g->inv_cell, hi = (float)kFineMax;
+        const float  ux = fminf(fmaxf((qx - g->ox) * inv, 0.0f), hi);
+        const float  uy = fminf(fmaxf((qy - g->oy) * inv, 0.0f), hi);
+        const float  uz = fminf(fmaxf((qz - g->oz) * inv, 0.0f), hi);
+        if (ux == ux && uy == uy && uz == uz)
+            key = fine_sort_key((uint32_t)ux, (uint32_t)uy, (uint32_t)uz);
+    }
+    const size_t o = (size_t)qoff[job] + slot;
+    keys[o] = ((unsigned long long)job << 37) | key;
+    vals[o] = slot;
+}
+
 __global__ void fill_u32_kernel(uint32_t* p, size_t n, uint32_t v)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -589,20 +647,62 @@ static int wait_cloud(Workspace* ws, const b200icp_cloud* c)
     return B200ICP_OK;
 }
 
+// Bins the queries of every job by the global fine cell of their transformed
+// position (one key kernel + one radix sort over all jobs of the wave).
+struct Binner
+{
+    unsigned long long *k0 = nullptr, *k1 = nullptr;
+    uint32_t *          v0 = nullptr, *v1 = nullptr, *qoff = nullptr;
+    void*               temp = nullptr;
+    size_t              temp_bytes = 0, total = 0, njobs = 0;
+    int                 end_bit = 37;
+    const uint32_t*     order = nullptr;  // queries of job j: order[qoff[j] ...]
+
+    int plan(size_t total_queries, size_t jobs, cudaStream_t s)
+    {
+        total = total_queries ? total_queries : 1;
+        njobs = jobs;
+        end_bit = 37;
+        while (end_bit < 64 && (1ull << (end_bit - 37)) < jobs) end_bit++;
+        cub::DoubleBuffer<unsigned long long> dk(nullptr, nullptr);
+        cub::DoubleBuffer<uint32_t>           dv(nullptr, nullptr);
+        B2_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, dk, dv, (int)total, 0, end_bit, s));
+        return B200ICP_OK;
+    }
+    void layout(Carver& c)
+    {
+        k0 = c.take<unsigned long long>(total), k1 = c.take<unsigned long long>(total);
+        v0 = c.take<uint32_t>(total), v1 = c.take<uint32_t>(total);
+        qoff = c.take<uint32_t>(njobs + 1);
+        temp = c.take<char>(temp_bytes);
+    }
+    int run(Workspace* ws, dim3 grid, const CloudView* d_clouds, const JobDev* d_jobs)
+    {
+        cudaStream_t s = ws->stream;
+        bin_key_kernel<<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, qoff, k0, v0);
+        cub::DoubleBuffer<unsigned long long> keys(k0, k1);
+        cub::DoubleBuffer<uint32_t>           vals(v0, v1);
+        B2_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, vals, (int)total, 0, end_bit, s));
+        order = vals.Current();
+        ws->launches += 1 + 1 + (end_bit + 7) / 8;
+        return B200ICP_OK;
+    }
+};
+
 template <bool WRITE>
 static void launch_match(Workspace* ws, uint32_t knn, dim3 grid, const CloudView* d_clouds,
-                         const JobDev* d_jobs, double* d_partials, uint32_t max_chunks,
-                         const IcpDevParams& D, const MatchOut& mo)
+                         const JobDev* d_jobs, const Binner& bin, double* d_partials,
+                         uint32_t max_chunks, const IcpDevParams& D, const MatchOut& mo)
 {
     if (knn == 6)
-        match_kernel<6, WRITE><<<grid, kChunk, 0, ws->stream>>>(d_clouds, d_jobs, d_partials,
-                                                                max_chunks, D, mo);
+        match_kernel<6, WRITE><<<grid, kChunk, 0, ws->stream>>>(d_clouds, d_jobs, bin.order, bin.qoff,
+                                                                d_partials, max_chunks, D, mo);
     else if (knn <= 4)
-        match_kernel<4, WRITE><<<grid, kChunk, 0, ws->stream>>>(d_clouds, d_jobs, d_partials,
-                                                                max_chunks, D, mo);
+        match_kernel<4, WRITE><<<grid, kChunk, 0, ws->stream>>>(d_clouds, d_jobs, bin.order, bin.qoff,
+                                                                d_partials, max_chunks, D, mo);
     else
-        match_kernel<8, WRITE><<<grid, kChunk, 0, ws->stream>>>(d_clouds, d_jobs, d_partials,
-                                                                max_chunks, D, mo);
+        match_kernel<8, WRITE><<<grid, kChunk, 0, ws->stream>>>(d_clouds, d_jobs, bin.order, bin.qoff,
+                                                                d_partials, max_chunks, D, mo);
     ws->launches++;
 }
 
@@ -666,12 +766,15 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
     for (auto& kv : cmap)
         if (int r = wait_cloud(ws, kv.first)) return r;
 
+    Binner bin;
+    if (int r = bin.plan(total_queries, n, s)) return r;
     Carver sz(nullptr);
     auto layout = [&](Carver& k, CloudView*& dc, JobDev*& dj, double*& dp, uint32_t*& da) {
         dc = k.take<CloudView>(views.size());
         dj = k.take<JobDev>(n);
         dp = k.take<double>((size_t)n * max_chunks * kNumMoments);
         da = k.take<uint32_t>(4);
+        bin.layout(k);
     };
     CloudView* d_clouds;
     JobDev*    d_jobs;
@@ -681,22 +784,26 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
     if (int r = ws->reserve_device(sz.off)) return r;
     Carver real(ws->d_scratch);
     layout(real, d_clouds, d_jobs, d_partials, d_active);
-    // pinned staging: views | jobs | active flags (2 slots) | n_active init
-    const size_t pin_bytes = align_up(views.size() * sizeof(CloudView)) +
-                             align_up(n * sizeof(JobDev)) + 256;
-    if (int r = ws->reserve_pinned(pin_bytes)) return r;
+    // pinned staging: views | jobs | query offsets | active flags (2 slots) | n_active init
+    const size_t off_jobs = align_up(views.size() * sizeof(CloudView));
+    const size_t off_qoff = off_jobs + align_up(n * sizeof(JobDev));
+    const size_t off_flags = off_qoff + align_up((n + 1) * sizeof(uint32_t));
+    if (int r = ws->reserve_pinned(off_flags + 256)) return r;
     char*      hp = (char*)ws->h_pinned;
     CloudView* h_views = (CloudView*)hp;
-    JobDev*    h_jobs = (JobDev*)(hp + align_up(views.size() * sizeof(CloudView)));
-    uint32_t*  h_flags = (uint32_t*)(hp + align_up(views.size() * sizeof(CloudView)) +
-                                    align_up(n * sizeof(JobDev)));
+    JobDev*    h_jobs = (JobDev*)(hp + off_jobs);
+    uint32_t*  h_qoff = (uint32_t*)(hp + off_qoff);
+    uint32_t*  h_flags = (uint32_t*)(hp + off_flags);
     memcpy(h_views, views.data(), views.size() * sizeof(CloudView));
     memcpy(h_jobs, hjobs.data(), n * sizeof(JobDev));
+    h_qoff[0] = 0;
+    for (size_t j = 0; j < n; j++) h_qoff[j + 1] = h_qoff[j] + (uint32_t)to[j]->n;
     h_flags[0] = h_flags[1] = 0xFFFFFFFFu;
     h_flags[2] = (uint32_t)n;
     B2_CUDA_TRY(cudaMemcpyAsync(d_clouds, h_views, views.size() * sizeof(CloudView),
                                 cudaMemcpyHostToDevice, s));
     B2_CUDA_TRY(cudaMemcpyAsync(d_jobs, h_jobs, n * sizeof(JobDev), cudaMemcpyHostToDevice, s));
+    B2_CUDA_TRY(cudaMemcpyAsync(bin.qoff, h_qoff, (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     B2_CUDA_TRY(cudaMemcpyAsync(d_active, h_flags + 2, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
 
     const bool prof = ctx->profile_on;
@@ -713,8 +820,12 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
         const uint32_t todo = std::min(kBatch, D.max_iterations - enq);
         for (uint32_t i = 0; i < todo; i++, enq++)
         {
+            // re-bin while the pose still moves by more than a fine cell (first
+            // iterations), then every 8th iteration
+            if (enq < 3 || (enq & 7u) == 0)
+                if (int r = bin.run(ws, mgrid, d_clouds, d_jobs)) return r;
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 0], s));
-            launch_match<false>(ws, D.knn, mgrid, d_clouds, d_jobs, d_partials, max_chunks, D, no_out);
+            launch_match<false>(ws, D.knn, mgrid, d_clouds, d_jobs, bin, d_partials, max_chunks, D, no_out);
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 1], s));
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 2], s));
             solve_kernel<<<(unsigned)n, kSolveThreads, 0, s>>>(d_clouds, d_jobs, d_partials, max_chunks, D,
@@ -736,7 +847,9 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
         batch++;
     }
     const dim3 qgrid(max_chunks, (unsigned)n);
-    quality_kernel<<<qgrid, kChunk, 0, s>>>(d_clouds, d_jobs, D);
+    if (D.max_iterations == 0)
+        if (int r = bin.run(ws, mgrid, d_clouds, d_jobs)) return r;
+    quality_kernel<<<qgrid, kChunk, 0, s>>>(d_clouds, d_jobs, bin.order, bin.qoff, D);
     covariance_kernel<<<(unsigned)n, 64, 0, s>>>(d_jobs, D);
     ws->launches += 2;
     B2_CUDA_TRY(cudaMemcpyAsync(h_jobs, d_jobs, n * sizeof(JobDev), cudaMemcpyDeviceToHost, s));
@@ -811,6 +924,56 @@ int run_align_batch(::b200icp* ctx, size_t n, const b200icp_cloud* const* from,
     return B200ICP_OK;
 }
 
+// one (from, to, pose) job laid out, uploaded and binned; `extra` carves the
+// caller's own arrays out of the same scratch allocation
+struct SingleJob
+{
+    CloudView* d_clouds = nullptr;
+    JobDev*    d_jobs = nullptr;
+    Binner     bin;
+    Pose       T;
+};
+
+template <typename F>
+static int single_job_setup(Workspace* ws, const b200icp_cloud* from, const b200icp_cloud* to,
+                            const double* pose6, uint32_t iter, SingleJob& sj, F&& extra)
+{
+    cudaStream_t s = ws->stream;
+    if (int r = wait_cloud(ws, from)) return r;
+    if (int r = wait_cloud(ws, to)) return r;
+    if (int r = sj.bin.plan(to->n, 1, s)) return r;
+    auto layout = [&](Carver& c) {
+        sj.d_clouds = c.take<CloudView>(2);
+        sj.d_jobs = c.take<JobDev>(1);
+        sj.bin.layout(c);
+        extra(c);
+    };
+    Carver sz(nullptr);
+    layout(sz);
+    if (int r = ws->reserve_device(sz.off)) return r;
+    Carver real(ws->d_scratch);
+    layout(real);
+    const size_t off_job = align_up(2 * sizeof(CloudView));
+    const size_t off_q = off_job + align_up(sizeof(JobDev));
+    if (int r = ws->reserve_pinned(off_q + 64)) return r;
+    CloudView* hv = (CloudView*)ws->h_pinned;
+    JobDev*    hj = (JobDev*)((char*)ws->h_pinned + off_job);
+    uint32_t*  hq = (uint32_t*)((char*)ws->h_pinned + off_q);
+    hv[0] = from->view(), hv[1] = to->view();
+    memset(hj, 0, sizeof(JobDev));
+    const double ident[6] = {0, 0, 0, 0, 0, 0};
+    pose_from_ypr(pose6 ? pose6 : ident, sj.T);
+    memcpy(hj->R, sj.T.R, sizeof(sj.T.R)), memcpy(hj->t, sj.T.t, sizeof(sj.T.t));
+    hj->from_cloud = 0, hj->to_cloud = 1;
+    hj->iter = iter;
+    hq[0] = 0, hq[1] = (uint32_t)to->n;
+    B2_CUDA_TRY(cudaMemcpyAsync(sj.d_clouds, hv, 2 * sizeof(CloudView), cudaMemcpyHostToDevice, s));
+    B2_CUDA_TRY(cudaMemcpyAsync(sj.d_jobs, hj, sizeof(JobDev), cudaMemcpyHostToDevice, s));
+    B2_CUDA_TRY(cudaMemcpyAsync(sj.bin.qoff, hq, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    const uint32_t chunks = (uint32_t)((to->n + kChunk - 1) / kChunk);
+    return sj.bin.run(ws, dim3(chunks ? chunks : 1, 1), sj.d_clouds, sj.d_jobs);
+}
+
 int run_knn(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, const double* pose6,
             uint32_t k, float max_dist, uint32_t* idx_out, float* d2_out)
 {
@@ -830,17 +993,14 @@ int run_knn(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, co
     cudaStream_t s = ws->stream;
     const size_t nq = q->n;
     if (nq == 0) return B200ICP_OK;
-    if (int r = wait_cloud(ws, ref)) return r;
-    if (int r = wait_cloud(ws, q)) return r;
-    Carver sz(nullptr);
-    sz.take<uint32_t>(nq * k), sz.take<float>(nq * k);
-    if (int r = ws->reserve_device(sz.off)) return r;
-    Carver    real(ws->d_scratch);
-    uint32_t* d_idx = real.take<uint32_t>(nq * k);
-    float*    d_d2 = real.take<float>(nq * k);
-    Pose      T;
-    const double ident[6] = {0, 0, 0, 0, 0, 0};
-    pose_from_ypr(pose6 ? pose6 : ident, T);
+    uint32_t* d_idx = nullptr;
+    float*    d_d2 = nullptr;
+    SingleJob sj;
+    if (int r = single_job_setup(ws, ref, q, pose6, 0, sj, [&](Carver& c) {
+            d_idx = c.take<uint32_t>(nq * k);
+            d_d2 = c.take<float>(nq * k);
+        }))
+        return r;
     const float cap_d2 = max_dist * max_dist;
     const int   fb = (int)((nq * k + 255) / 256);
     fill_u32_kernel<<<fb, 256, 0, s>>>(d_idx, nq * k, kInvalid);
@@ -852,15 +1012,17 @@ int run_knn(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, co
         if (int r = ws->reserve_prof_events(1)) return r;
         B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[0], s));
     }
-    const int blocks = (int)((nq + kChunk - 1) / kChunk);
+    const int             blocks = (int)((nq + kChunk - 1) / kChunk);
+    const CloudView       vr = ref->view(), vq = q->view();
+    const uint32_t* const ord = sj.bin.order;
     if (k == 1)
-        knn_kernel<1><<<blocks, kChunk, 0, s>>>(ref->view(), q->view(), T, k, cap_d2, d_idx, d_d2);
+        knn_kernel<1><<<blocks, kChunk, 0, s>>>(vr, vq, ord, sj.T, k, cap_d2, d_idx, d_d2);
     else if (k <= 4)
-        knn_kernel<4><<<blocks, kChunk, 0, s>>>(ref->view(), q->view(), T, k, cap_d2, d_idx, d_d2);
+        knn_kernel<4><<<blocks, kChunk, 0, s>>>(vr, vq, ord, sj.T, k, cap_d2, d_idx, d_d2);
     else if (k <= 6)
-        knn_kernel<6><<<blocks, kChunk, 0, s>>>(ref->view(), q->view(), T, k, cap_d2, d_idx, d_d2);
+        knn_kernel<6><<<blocks, kChunk, 0, s>>>(vr, vq, ord, sj.T, k, cap_d2, d_idx, d_d2);
     else
-        knn_kernel<8><<<blocks, kChunk, 0, s>>>(ref->view(), q->view(), T, k, cap_d2, d_idx, d_d2);
+        knn_kernel<8><<<blocks, kChunk, 0, s>>>(vr, vq, ord, sj.T, k, cap_d2, d_idx, d_d2);
     ws->launches++;
     if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[1], s));
     B2_CUDA_TRY(cudaGetLastError());
@@ -894,49 +1056,27 @@ int run_match(::b200icp* ctx, const b200icp_cloud* from, const b200icp_cloud* to
     const size_t        n = to->n, k = D.knn;
     if (n_pairings) *n_pairings = 0;
     if (n == 0) return B200ICP_OK;
-    if (int r = wait_cloud(ws, from)) return r;
-    if (int r = wait_cloud(ws, to)) return r;
     const uint32_t max_chunks = (uint32_t)((n + kChunk - 1) / kChunk);
-    CloudView*     d_clouds;
-    JobDev*        d_jobs;
-    double*        d_partials;
-    uint32_t*      d_active;
+    double*        d_partials = nullptr;
     MatchOut       mo;
-    auto layout = [&](Carver& c) {
-        d_clouds = c.take<CloudView>(2);
-        d_jobs = c.take<JobDev>(1);
-        d_partials = c.take<double>((size_t)max_chunks * kNumMoments);
-        d_active = c.take<uint32_t>(4);
-        mo.paired = c.take<uint8_t>(n);
-        mo.nn_idx = c.take<uint32_t>(n * k);
-        mo.nn_cnt = c.take<uint32_t>(n);
-        mo.centroid = c.take<double>(n * 3);
-        mo.normal = c.take<double>(n * 3);
-    };
-    Carver sz(nullptr);
-    layout(sz);
-    if (int r = ws->reserve_device(sz.off)) return r;
-    Carver real(ws->d_scratch);
-    layout(real);
-    if (int r = ws->reserve_pinned(2 * sizeof(CloudView) + sizeof(JobDev) + 64)) return r;
-    CloudView* hv = (CloudView*)ws->h_pinned;
-    JobDev*    hj = (JobDev*)((char*)ws->h_pinned + align_up(2 * sizeof(CloudView)));
-    hv[0] = from->view(), hv[1] = to->view();
-    memset(hj, 0, sizeof(JobDev));
-    Pose         T;
-    const double ident[6] = {0, 0, 0, 0, 0, 0};
-    pose_from_ypr(pose6 ? pose6 : ident, T);
-    memcpy(hj->R, T.R, sizeof(T.R)), memcpy(hj->t, T.t, sizeof(T.t));
-    hj->from_cloud = 0, hj->to_cloud = 1;
-    hj->iter = D.run_from_iteration;  // the matcher is active at this iteration
-    B2_CUDA_TRY(cudaMemcpyAsync(d_clouds, hv, 2 * sizeof(CloudView), cudaMemcpyHostToDevice, s));
-    B2_CUDA_TRY(cudaMemcpyAsync(d_jobs, hj, sizeof(JobDev), cudaMemcpyHostToDevice, s));
+    SingleJob      sj;
+    // the matcher is active at iteration run_from_iteration
+    if (int r = single_job_setup(ws, from, to, pose6, D.run_from_iteration, sj, [&](Carver& c) {
+            d_partials = c.take<double>((size_t)max_chunks * kNumMoments);
+            mo.paired = c.take<uint8_t>(n);
+            mo.nn_idx = c.take<uint32_t>(n * k);
+            mo.nn_cnt = c.take<uint32_t>(n);
+            mo.centroid = c.take<double>(n * 3);
+            mo.normal = c.take<double>(n * 3);
+        }))
+        return r;
     B2_CUDA_TRY(cudaMemsetAsync(mo.paired, 0, n, s));
     B2_CUDA_TRY(cudaMemsetAsync(mo.nn_cnt, 0, n * sizeof(uint32_t), s));
     B2_CUDA_TRY(cudaMemsetAsync(mo.nn_idx, 0xFF, n * k * sizeof(uint32_t), s));
     B2_CUDA_TRY(cudaMemsetAsync(mo.centroid, 0, n * 3 * sizeof(double), s));
     B2_CUDA_TRY(cudaMemsetAsync(mo.normal, 0, n * 3 * sizeof(double), s));
-    launch_match<true>(ws, D.knn, dim3(max_chunks, 1), d_clouds, d_jobs, d_partials, max_chunks, D, mo);
+    launch_match<true>(ws, D.knn, dim3(max_chunks, 1), sj.d_clouds, sj.d_jobs, sj.bin, d_partials,
+                       max_chunks, D, mo);
     B2_CUDA_TRY(cudaGetLastError());
     std::vector<double> part((size_t)max_chunks * kNumMoments);
     B2_CUDA_TRY(cudaMemcpyAsync(part.data(), d_partials, part.size() * sizeof(double),

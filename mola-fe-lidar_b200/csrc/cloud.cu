@@ -31,15 +31,6 @@ __device__ __forceinline__ float dec_f(uint32_t e)
     return __uint_as_float(u);
 }
 
-__device__ __forceinline__ uint32_t spread10(uint32_t v)
-{
-    v &= 0x3FFu;
-    v = (v | (v << 16)) & 0x030000FFu;
-    v = (v | (v << 8)) & 0x0300F00Fu;
-    v = (v | (v << 4)) & 0x030C30C3u;
-    v = (v | (v << 2)) & 0x09249249u;
-    return v;
-}
 __device__ __forceinline__ uint32_t compact10(uint32_t v)
 {
     v &= 0x09249249u;
@@ -107,7 +98,6 @@ __global__ void grid_setup_kernel(const uint32_t* __restrict__ bb, float block_r
     for (int d = 0; d < 3; d++) g->bmin[d] = mn[d], g->bmax[d] = mx[d];
 }
 
-constexpr unsigned long long kInvalidSortKey = 1ull << 36;
 
 // sort key = (Morton30 of the block) << 6 | fine cell inside the block
 __global__ void cell_key_kernel(const float* __restrict__ x, const float* __restrict__ y,
@@ -125,9 +115,7 @@ __global__ void cell_key_kernel(const float* __restrict__ x, const float* __rest
         const uint32_t fx = (uint32_t)min(max((int)floorf((px - g->ox) * inv), 0), kFineMax);
         const uint32_t fy = (uint32_t)min(max((int)floorf((py - g->oy) * inv), 0), kFineMax);
         const uint32_t fz = (uint32_t)min(max((int)floorf((pz - g->oz) * inv), 0), kFineMax);
-        const uint32_t mort = spread10(fx >> 2) | (spread10(fy >> 2) << 1) | (spread10(fz >> 2) << 2);
-        const uint32_t sub = (fx & 3u) | ((fy & 3u) << 2) | ((fz & 3u) << 4);
-        key = ((unsigned long long)mort << 6) | sub;
+        key = fine_sort_key(fx, fy, fz);
     }
     keys[i] = key;
     vals[i] = i;

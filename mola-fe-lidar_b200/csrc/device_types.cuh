@@ -98,4 +98,26 @@ __host__ __device__ inline uint32_t hash_slot(uint32_t key, uint32_t shift)
     return (key * 2654435761u) >> shift;
 }
 
+// 10 bits -> every third bit (Morton interleave helper)
+__host__ __device__ inline uint32_t spread10(uint32_t v)
+{
+    v &= 0x3FFu;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+// Sort key of a fine cell (fx,fy,fz in [0, kFineMax]): Morton code of its
+// block in the high bits, position inside the block in the low 6 bits -- the
+// memory order of the index, and the order queries are binned in.
+constexpr unsigned long long kInvalidSortKey = 1ull << 36;
+__host__ __device__ inline unsigned long long fine_sort_key(uint32_t fx, uint32_t fy, uint32_t fz)
+{
+    const uint32_t mort = spread10(fx >> 2) | (spread10(fy >> 2) << 1) | (spread10(fz >> 2) << 2);
+    const uint32_t sub = (fx & 3u) | ((fy & 3u) << 2) | ((fz & 3u) << 4);
+    return ((unsigned long long)mort << 6) | sub;
+}
+
 }  // namespace b2

@@ -333,6 +333,82 @@ B2_HD int qr_solve6(const double* Ain, const double* bin, double* x)
     return rank;
 }
 
+B2_HD int inverse6(const double* A, double* Ainv);
+
+// Cholesky solve of a symmetric positive definite 6x6 system. Every index is
+// a compile-time constant after unrolling, so on the device the factor lives
+// in registers (the pivoted QR above indexes dynamically and goes through
+// local memory). Returns false when a pivot is not safely positive: the
+// caller then falls back to the rank-revealing QR.
+B2_HD bool chol_solve6(const double* H, const double* b, double* x)
+{
+    double L[6][6];
+    double dmax = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) dmax = fmax(dmax, H[i * 6 + i]);
+    const double tiny = 1e-13 * dmax;
+#pragma unroll
+    for (int j = 0; j < 6; j++)
+    {
+        double s = H[j * 6 + j];
+#pragma unroll
+        for (int k = 0; k < j; k++) s -= L[j][k] * L[j][k];
+        if (!(s > tiny)) return false;
+        const double d = sqrt(s);
+        const double inv = 1.0 / d;
+        L[j][j] = d;
+#pragma unroll
+        for (int i = j + 1; i < 6; i++)
+        {
+            double t = H[i * 6 + j];
+#pragma unroll
+            for (int k = 0; k < j; k++) t -= L[i][k] * L[j][k];
+            L[i][j] = t * inv;
+        }
+    }
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+    {
+        double s = b[i];
+#pragma unroll
+        for (int k = 0; k < i; k++) s -= L[i][k] * y[k];
+        y[i] = s / L[i][i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; i--)
+    {
+        double s = y[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; k++) s -= L[k][i] * x[k];
+        x[i] = s / L[i][i];
+    }
+    return true;
+}
+
+// 6x6 solve used by the Gauss-Newton step: Cholesky when H is safely positive
+// definite, else the rank-revealing QR (degenerate geometry)
+B2_HD void solve6_spd(const double* H, const double* b, double* x)
+{
+    if (!chol_solve6(H, b, x)) qr_solve6(H, b, x);
+}
+
+// inverse of a symmetric 6x6: Cholesky column by column, QR on failure
+B2_HD int inverse6_spd(const double* A, double* Ainv)
+{
+    bool ok = true;
+#pragma unroll 1
+    for (int c = 0; c < 6 && ok; c++)
+    {
+        double e[6] = {0, 0, 0, 0, 0, 0}, x[6];
+        e[c] = 1.0;
+        ok = chol_solve6(A, e, x);
+        for (int i = 0; i < 6; i++) Ainv[i * 6 + c] = x[i];
+    }
+    if (ok) return 6;
+    return inverse6(A, Ainv);
+}
+
 B2_HD int inverse6(const double* A, double* Ainv)
 {
     int rank = 6;

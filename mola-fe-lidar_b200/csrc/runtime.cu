@@ -23,7 +23,10 @@ int Workspace::init(int dev)
 {
     device = dev;
     B2_CUDA_TRY(cudaSetDevice(dev));
-    B2_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    // a BLOCKING stream: it orders against the legacy default stream, so a
+    // harness can bracket library work with events recorded on stream 0
+    // (bench.py does); streams of different workspaces still run concurrently
+    B2_CUDA_TRY(cudaStreamCreate(&stream));
     for (auto& e : ev) B2_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return B200ICP_OK;
 }

@@ -1,0 +1,202 @@
+// LidarOdometry.h -- host-side mirror of mola::LidarOdometry
+// (reference: include/mola-fe-lidar/LidarOdometry.h:29-192), same public
+// interface, parameter block, state and job types; the ICP seam
+// (mp2p_icp::ICP::Ptr + mp2p_icp::Parameters, h:96-102) is the C ABI of
+// include/b200icp.h and metric_map_t::Ptr is a cloud resident in HBM.
+#pragma once
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../csrc/icp_math.cuh"
+#include "mola_stubs.h"
+#include "util.h"
+
+namespace mola
+{
+using CPose3D = b2::Pose;  // mrpt::poses::CPose3D: rotation matrix + translation
+
+inline CPose3D pose_identity()
+{
+    CPose3D p;
+    for (int i = 0; i < 9; i++) p.R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    p.t[0] = p.t[1] = p.t[2] = 0;
+    return p;
+}
+inline CPose3D  to_CPose3D(const TPose3D& p)
+{
+    const double v[6] = {p.x, p.y, p.z, p.yaw, p.pitch, p.roll};
+    CPose3D      o;
+    b2::pose_from_ypr(v, o);
+    return o;
+}
+inline TPose3D asTPose(const CPose3D& p)
+{
+    double v[6];
+    b2::pose_to_ypr(p, v);
+    return TPose3D{v[0], v[1], v[2], v[3], v[4], v[5]};
+}
+inline double pose_norm(const CPose3D& p) { return std::sqrt(p.t[0] * p.t[0] + p.t[1] * p.t[1] + p.t[2] * p.t[2]); }
+
+/** mrpt::poses::CPose3DPDFGaussian: mean + 6x6 covariance (x y z yaw pitch roll) */
+struct CPose3DPDFGaussian
+{
+    CPose3D mean = pose_identity();
+    double  cov[36] = {0};
+    const CPose3D& getMeanVal() const { return mean; }
+};
+
+/** mrpt::graphs::CNetworkOfPoses3D reduced to what cpp:459-464, 531-569,
+ *  674-675 and 833-837 use. */
+struct NetworkOfPoses3D
+{
+    id_t                                    root = INVALID_ID;
+    std::map<id_t, CPose3D>                 nodes;
+    std::map<std::pair<id_t, id_t>, CPose3D> edges;
+    void insertEdgeAtEnd(id_t from, id_t to, const CPose3D& p) { edges[{from, to}] = p; }
+    /** spanning tree from `root` over unit-weight edges: node poses wrt the
+     *  root and topological distances (dijkstra_nodes_estimate, cpp:542) */
+    void dijkstra_nodes_estimate(std::map<id_t, size_t>& topo_dists);
+    void getAdjacencyMatrix(std::map<id_t, std::set<id_t>>& adj) const;
+};
+
+class LidarOdometry : public FrontEndBase
+{
+   public:
+    LidarOdometry();
+    ~LidarOdometry() override;
+
+    // See docs in base class (reference h:38-43)
+    void initialize(const Yaml& cfg) override;
+    void spinOnce() override;
+    void onNewObservation(CObservation::Ptr& o) override;
+
+    /** Re-initializes the front-end */
+    void reset();
+
+    enum class AlignKind : uint8_t
+    {
+        LidarOdometry,
+        NearbyAlign,
+        LoopClosure
+    };
+
+    struct Parameters
+    {
+        double min_time_between_scans{0.2};
+        double min_dist_xyz_between_keyframes{1.0};
+        double min_rotation_between_keyframes{30.0 * 3.14159265358979323846 / 180.0};
+        double min_icp_goodness{0.4};
+        double min_icp_goodness_lc{0.6};
+
+        // vestigial in the reference (never loaded, h:76-80)
+        unsigned int full_pointcloud_decimation{20};
+        double       voxel_filter_resolution{.5};
+        unsigned int voxel_filter_decimation{1};
+
+        double       min_dist_to_matching{6.0};
+        double       max_dist_to_matching{12.0};
+        double       max_dist_to_loop_closure{30.0};
+        unsigned int loop_closure_montecarlo_samples{10};
+        unsigned int max_nearby_align_checks{2};
+        unsigned int min_topo_dist_to_consider_loopclosure{20};
+        unsigned int max_KFs_local_graph{50000};
+
+        /** the ICP object and its parameters for one alignment case (h:96-102) */
+        struct ICP_case
+        {
+            b200icp_t*       icp = nullptr;
+            b200icp_params_t icpParameters;
+        };
+        std::map<AlignKind, ICP_case> icp;
+
+        int   viz_decor_decimation{5};
+        float viz_decor_pointsize{2.0f};
+
+        /** harness-supplied `pointcloud_filter` block (cpp:139-140): voxel
+         *  decimation stage, 0 = empty pipeline */
+        double voxel_decimation_resolution{0.0};
+        bool   voxel_use_average{false};
+        /** seed of the Monte-Carlo guesses (the reference default-constructs
+         *  an unseeded generator, cpp:773) */
+        uint64_t montecarlo_seed{1};
+        int      device{0};
+    };
+    Parameters params_;
+
+    using topological_dist_t = std::size_t;
+
+    struct ICP_Input
+    {
+        using Ptr = std::shared_ptr<ICP_Input>;
+        AlignKind        align_kind{AlignKind::LidarOdometry};
+        id_t             to_id{INVALID_ID};
+        id_t             from_id{INVALID_ID};
+        DeviceCloud::Ptr to_pc, from_pc;
+        TPose3D          init_guess_to_wrt_from;
+        b200icp_params_t icp_params;
+        std::string      debug_str;
+    };
+    struct ICP_Output
+    {
+        double             goodness{.0};
+        CPose3DPDFGaussian found_pose_to_wrt_from;
+        uint32_t           n_iterations{0}, termination_reason{0};
+    };
+    void run_one_icp(const ICP_Input& in, ICP_Output& out);
+
+    struct MethodState
+    {
+        double           last_obs_tim{-1.0};  // < 0: none yet
+        DeviceCloud::Ptr last_points{};
+        TTwist3D         last_iter_twist;
+        bool             last_iter_twist_is_good{false};
+        id_t             last_kf{INVALID_ID};
+        CPose3D          accum_since_last_kf = pose_identity();
+
+        struct LocalPoseGraph
+        {
+            NetworkOfPoses3D                graph;
+            std::set<std::pair<id_t, id_t>> checked_KF_pairs;
+        };
+        LocalPoseGraph local_pose_graph;
+        int            kf_decor_decim_cnt{-1};
+
+        // bookkeeping for harnesses (not in the reference)
+        ICP_Output last_icp_out;
+        size_t     n_processed{0}, n_dropped{0}, n_icp{0};
+    };
+
+    const MethodState& state() const { return state_; }
+    MethodState        stateCopy() const { return state_; }
+
+    /** blocks until both worker pools are idle (harness helper) */
+    void waitIdle();
+    WorldModel::Ptr worldmodel() { return worldmodel_; }
+    void            setWorldModel(WorldModel::Ptr w) { worldmodel_ = std::move(w); }
+    TimeLogger      profiler_;
+
+    /** Here happens the actual processing (public for harnesses that want the
+     *  synchronous path; the reference invokes it from worker_pool_) */
+    void doProcessNewObservation(CObservation::Ptr& o);
+    void doCheckForNonAdjacentKFs(ICP_Input::Ptr d);
+
+   private:
+    WorkerThreadsPool worker_pool_{1};
+    WorkerThreadsPool worker_pool_past_KFs_{1};
+
+    MethodState     state_;
+    WorldModel::Ptr worldmodel_;
+
+    void checkForNearbyKFs();
+    void release_icp_objects();
+    DeviceCloud::Ptr make_cloud(const CObservation& o);
+
+    std::mutex local_pose_graph_mtx;
+    float      cloud_search_radius_{0.f};
+};
+
+}  // namespace mola

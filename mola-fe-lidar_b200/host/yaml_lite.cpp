@@ -223,6 +223,17 @@ struct Parser
         {
             const std::string& t = lines[pos].text;
             const size_t       c = key_colon(t);
+            if (c == std::string::npos && t.compare(0, 9, "$include{") == 0)
+            {
+                // a whole-line $include{} inside a map: merge the file's entries
+                Node inc = value_from_text(t);
+                if (!inc.isMap() && !inc.isNull())
+                    throw std::runtime_error("yaml: line " + std::to_string(lines[pos].number) +
+                                             ": $include{} inside a map must yield a map");
+                for (auto& kv : inc.map) n.map.push_back(std::move(kv));
+                pos++;
+                continue;
+            }
             if (c == std::string::npos)
                 throw std::runtime_error("yaml: line " + std::to_string(lines[pos].number) +
                                          ": expected 'key: value', got: " + t);

@@ -1,0 +1,143 @@
+"""The LidarOdometry module (host C++ mirror over the C ABI) against a Python
+restatement of the reference control flow (LidarOdometry.cpp:201-339) that
+uses the oracle's ICP: same per-scan poses, twist, keyframes and factors."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_T, TOL_R = 1e-5, 1e-6
+
+
+def _sequence(n_scans, n_pts=30000, seed=1):
+    from mola_fe_lidar_b200 import scene
+    scans, poses = scene.make_sequence(n_scans, seed=seed)
+    rng = np.random.default_rng(seed)
+    sub = [s[np.sort(rng.choice(len(s), n_pts, replace=False))] for s in scans]
+    return sub, poses
+
+
+def _compose(a, b, oracle):
+    Ra, ta = oracle.pose_to_Rt(a)
+    Rb, tb = oracle.pose_to_Rt(b)
+    return oracle.Rt_to_pose(Ra @ Rb, Ra @ tb + ta)
+
+
+def _reference_flow(oracle, scans, stamps, min_dist=3.0, min_rot=np.deg2rad(30.0), min_good=0.5,
+                    min_dt=0.01, voxel=None):
+    """cpp:201-339 with the oracle as mp2p_icp."""
+    prm = oracle.default_params()
+    last_t, last_cloud, twist, twist_good = None, None, np.zeros(4), False
+    accum, out, kfs = np.zeros(6), [], []
+    for s, t in zip(scans, stamps):
+        if last_t is not None and (t - last_t) < min_dt:
+            out.append(None)
+            continue
+        pts = s if voxel is None else oracle.voxel_decimate(s, voxel)[1]
+        cloud = oracle.Cloud(pts)
+        prev_t, prev_cloud = last_t, last_cloud
+        last_t, last_cloud = t, cloud
+        if prev_cloud is None:
+            kfs.append(t)
+            out.append(None)
+            continue
+        dt = t - prev_t
+        guess = np.array([twist[0] * dt, twist[1] * dt, twist[2] * dt, twist[3] * dt, 0, 0])
+        r = oracle.icp_align(prev_cloud, cloud, guess, prm, kdtree=True)
+        p = r["pose"]
+        twist, twist_good = np.array([p[0] / dt, p[1] / dt, p[2] / dt, p[3] / dt]), True
+        accum = _compose(accum, p, oracle)
+        R, tt = oracle.pose_to_Rt(accum)
+        rot = np.linalg.norm(oracle.se3_log(R, tt)[3:])
+        if r["quality"] > min_good and (np.linalg.norm(accum[:3]) > min_dist or rot > min_rot):
+            kfs.append(t)
+            accum = np.zeros(6)
+        out.append(r)
+    return out, kfs, accum, twist
+
+
+def test_module_params_from_shipped_yaml():
+    from mola_fe_lidar_b200 import lidar_odometry as lom
+    lo = lom.LidarOdometry(yaml_text=lom.system_yaml())
+    p = lo.params()
+    assert float(p["min_time_between_scans"]) == 0.01 and float(p["min_dist_xyz_between_keyframes"]) == 3
+    assert float(p["min_icp_goodness"]) == 0.5 and float(p["min_icp_goodness_lc"]) == 0.7
+    assert float(p["min_dist_to_matching"]) == 5 and float(p["max_dist_to_matching"]) == 20
+    assert float(p["max_dist_to_loop_closure"]) == 30 and int(p["max_nearby_align_checks"]) == 5
+    assert int(p["min_topo_dist_to_consider_loopclosure"]) == 30
+    assert int(p["loop_closure_montecarlo_samples"]) == 10
+    assert abs(float(p["min_rotation_between_keyframes"]) - np.deg2rad(30)) < 1e-12  # header default
+    for k in range(3):
+        assert int(p[f"icp[{k}].maxIterations"]) == 100 and float(p[f"icp[{k}].distanceThreshold"]) == 0.7
+    lo.close()
+    with pytest.raises(Exception, match="min_dist_xyz_between_keyframes"):
+        lom.LidarOdometry(yaml_text="raw_sensor_label: lidar\nparams:\n  min_icp_goodness: 0.5\n")
+
+
+@pytest.mark.parametrize("voxel", [None, 0.5])
+def test_scan_to_scan_flow_matches_oracle(oracle, voxel):
+    from mola_fe_lidar_b200 import lidar_odometry as lom
+    scans, poses = _sequence(7)
+    stamps = [0.1 * i for i in range(7)]
+    lo = lom.LidarOdometry(yaml_text=lom.system_yaml(voxel_resolution=voxel))
+    ref, kfs, accum, twist = _reference_flow(oracle, scans, stamps, voxel=voxel)
+    n_icp = 0
+    for s, t, r in zip(scans, stamps, ref):
+        lo.onNewObservation(s, t, sync=True)
+        st = lo.state()
+        if r is None:
+            continue
+        n_icp += 1
+        assert st["n_icp"] == n_icp
+        assert np.abs(st["last_icp_pose"][:3] - r["pose"][:3]).max() < TOL_T
+        assert np.abs(st["last_icp_pose"][3:] - r["pose"][3:]).max() < TOL_R
+        assert st["last_icp_goodness"] == r["quality"]
+        assert st["last_icp_iterations"] == r["n_iterations"]
+        assert st["last_icp_termination"] == r["termination_reason"]
+    lo.wait_idle()
+    st = lo.state()
+    assert st["n_keyframes"] == len(kfs) >= 2
+    assert np.abs(st["accum_since_last_kf"][:3] - accum[:3]).max() < 5e-5
+    assert np.abs(st["last_twist"][[0, 1, 2, 5]] - twist).max() < 1e-3
+    assert st["last_iter_twist_is_good"] == 1
+    f = lo.factors()
+    assert len(f) >= len(kfs) - 1 and f[0][0] == 0 and f[0][1] == 1
+    lo.close()
+
+
+def test_time_gate_label_filter_and_async_queue():
+    from mola_fe_lidar_b200 import lidar_odometry as lom
+    scans, _ = _sequence(3, n_pts=8000)
+    lo = lom.LidarOdometry(yaml_text=lom.system_yaml())
+    lo.onNewObservation(scans[0], 0.0, sync=True)
+    lo.onNewObservation(scans[1], 0.005, sync=True)          # < min_time_between_scans: dropped
+    lo.onNewObservation(scans[1], 0.5, label="camera", sync=True)  # not "my" sensor
+    st = lo.state()
+    assert st["n_processed"] == 1 and st["n_dropped"] == 1 and st["n_icp"] == 0
+    lo.onNewObservation(scans[1], 0.1)                       # asynchronous path (worker pool)
+    lo.onNewObservation(scans[2], 0.2)
+    lo.wait_idle()
+    st = lo.state()
+    assert st["n_processed"] == 3 and st["n_icp"] == 2 and st["last_obs_tim"] == 0.2
+    prof = lo.profile()
+    assert prof["doProcessNewObservation.3.icp_latest"][0] == 2 and "run_one_icp" in prof
+    lo.reset()
+    assert lo.state()["n_processed"] == 0 and lo.state()["last_points_size"] == 0
+    lo.close()
+
+
+def test_extra_edges_between_nearby_keyframes(oracle):
+    """checkForNearbyKFs + doCheckForNonAdjacentKFs (cpp:516-849): KFs >= 5 m apart get an extra factor."""
+    from mola_fe_lidar_b200 import lidar_odometry as lom, scene
+    scans, poses = _sequence(14, n_pts=20000)
+    lo = lom.LidarOdometry(yaml_text=lom.system_yaml())
+    for i, s in enumerate(scans):
+        lo.onNewObservation(s, 0.1 * i, sync=True)
+    lo.wait_idle()
+    st = lo.state()
+    f = lo.factors()
+    assert st["n_keyframes"] >= 3 and st["n_checked_pairs"] >= 1
+    extra = [x for x in f if abs(int(x[1]) - int(x[0])) > 1]
+    assert len(extra) >= 1, "expected at least one non-adjacent KF edge"
+    assert st["n_factors"] == len(f) and st["n_localizations"] == 14
+    lo.close()

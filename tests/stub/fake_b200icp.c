@@ -1,0 +1,83 @@
+/* fake_b200icp.c -- TEST DOUBLE of the device side of include/b200icp.h, used
+ * only by tests/test_host_logic_cpu.py through LD_PRELOAD so that the C++ host
+ * module (LidarOdometry mirror) can be exercised on a box without a GPU.
+ * It is not a CPU fallback of the product: it computes nothing.  A "cloud"
+ * remembers its size and its first point; "align" reports the translation
+ * between the first points of the two clouds (so a test can script the
+ * odometry it wants the front-end logic to see) with quality taken from the
+ * first point's z coordinate of the `to` cloud (z0 >= 0 ? 1.0 : 0.1). */
+#include <stdlib.h>
+#include <string.h>
+#include "../../include/b200icp.h"
+
+struct b200icp { b200icp_params_t P; };
+struct b200icp_cloud { size_t n; float p0[3]; };
+static unsigned long g_align_calls = 0, g_batch_calls = 0, g_voxel_calls = 0;
+
+int b200icp_device_count(void) { return 1; }
+int b200icp_create(const b200icp_params_t* p, int device, b200icp_t** out)
+{
+    (void)device;
+    b200icp_t* o = (b200icp_t*)calloc(1, sizeof(*o));
+    if (p) o->P = *p;
+    *out = o;
+    return B200ICP_OK;
+}
+void b200icp_destroy(b200icp_t* icp) { free(icp); }
+int b200icp_cloud_upload(b200icp_t* icp, const float* x, const float* y, const float* z, size_t n,
+                         float search_radius, b200icp_cloud_t** out)
+{
+    (void)icp, (void)search_radius;
+    b200icp_cloud_t* c = (b200icp_cloud_t*)calloc(1, sizeof(*c));
+    c->n = n;
+    if (n) c->p0[0] = x[0], c->p0[1] = y[0], c->p0[2] = z[0];
+    *out = c;
+    return B200ICP_OK;
+}
+void   b200icp_cloud_free(b200icp_cloud_t* c) { free(c); }
+size_t b200icp_cloud_size(const b200icp_cloud_t* c) { return c ? c->n : 0; }
+int b200icp_voxel_decimate(b200icp_t* icp, const b200icp_cloud_t* in, float resolution, int use_average,
+                           float search_radius, b200icp_cloud_t** out, uint32_t* keep_idx)
+{
+    (void)icp, (void)resolution, (void)use_average, (void)search_radius, (void)keep_idx;
+    b200icp_cloud_t* c = (b200icp_cloud_t*)calloc(1, sizeof(*c));
+    *c = *in;
+    c->n = in->n / 2; /* visible effect of the filter stage */
+    *out = c;
+    g_voxel_calls++;
+    return B200ICP_OK;
+}
+static void fake_result(const b200icp_cloud_t* from, const b200icp_cloud_t* to, const double* guess,
+                        b200icp_result_t* r)
+{
+    memset(r, 0, sizeof(*r));
+    for (int i = 0; i < 3; i++) r->pose[i] = (double)to->p0[i] - (double)from->p0[i];
+    r->pose[2] = 0.0;
+    r->pose[3] = guess ? guess[3] : 0.0; /* yaw: echo the guess */
+    r->R[0] = r->R[4] = r->R[8] = 1.0;
+    for (int i = 0; i < 3; i++) r->t[i] = r->pose[i];
+    for (int i = 0; i < 6; i++) r->cov[i * 7] = 1e-4;
+    r->quality = to->p0[2] >= 0.f ? 1.0 : 0.1;
+    r->n_iterations = 3;
+    r->termination_reason = B200ICP_TERM_STALLED;
+    r->n_pairings = (uint32_t)to->n;
+}
+int b200icp_align(b200icp_t* icp, const b200icp_cloud_t* from, const b200icp_cloud_t* to,
+                  const double guess6[6], b200icp_result_t* out)
+{
+    (void)icp;
+    g_align_calls++;
+    fake_result(from, to, guess6, out);
+    return B200ICP_OK;
+}
+int b200icp_align_batch(b200icp_t* icp, size_t n, const b200icp_cloud_t* const* from,
+                        const b200icp_cloud_t* const* to, const double* guesses6, b200icp_result_t* out)
+{
+    (void)icp;
+    g_batch_calls++;
+    for (size_t i = 0; i < n; i++) fake_result(from[i], to[i], guesses6 + 6 * i, out + i);
+    return B200ICP_OK;
+}
+unsigned long fake_align_calls(void) { return g_align_calls; }
+unsigned long fake_batch_calls(void) { return g_batch_calls; }
+unsigned long fake_voxel_calls(void) { return g_voxel_calls; }

@@ -20,10 +20,8 @@
 // perturbation T (+) exp(eps).  One pass over the pairings per OUTER iteration
 // instead of one per inner iteration; the iterates equal the reference's
 // per-pairing Gauss-Newton in exact arithmetic.
-#include <cub/device/device_radix_sort.cuh>
-
 #include "icp_math.cuh"
-#include "knn_search.cuh"
+#include "tile_search.cuh"
 #include "runtime.cuh"
 
 #include <algorithm>
@@ -32,31 +30,37 @@
 
 namespace b2
 {
-// index tables for the symmetric 3x3 (nn) and 4x4 (hh) products
-__device__ __forceinline__ int sym3(int i, int k)
+// ---- moments ---------------------------------------------------------------
+// Every pairing contributes e e^T with the 16-vector
+//   e = [ a (12) | r0 | 1 | 0 | 0 ],  a[4 i + j] = n_i * h_j,  h = (p_local, 1)
+// so S = sum e e^T (16x16, symmetric) holds A = sum a a^T (12x12), sum a r0
+// (column 12), sum r0^2 (S[12][12]) and the pairing count (S[13][13]).  S is
+// accumulated on the FP64 tensor-core path (DMMA m8n8k4): per 4 pairings the
+// warp loads two fragments from its staging buffer and issues three MMAs for
+// the tiles C00 = E[0:8] E[0:8]^T, C01 = E[0:8] E[8:16]^T, C11 = E[8:16] E[8:16]^T
+// (C10 = C01^T is not needed).  The accumulators stay in registers over all the
+// items a CTA processes; the order of accumulation is fixed by the static
+// item -> CTA assignment, so runs are bit-reproducible.
+constexpr int kStageStride = 20;  // doubles per staged row: conflict-free fragment loads
+
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b)
 {
-    if (i > k)
-    {
-        const int t = i;
-        i = k, k = t;
-    }
-    return (i == 0) ? k : (i == 1 ? 2 + k : 5);  // 00 01 02 11 12 22
-}
-__device__ __forceinline__ int sym4(int j, int l)
-{
-    if (j > l)
-    {
-        const int t = j;
-        j = l, l = t;
-    }
-    return (j == 0) ? l : (j == 1 ? 3 + l : (j == 2 ? 5 + l : 9));  // 00 01 02 03 11 12 13 22 23 33
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
 }
 
-__device__ __forceinline__ double warp_sum(double v)
+// element (a, b) of S from the three stored tiles (64 doubles each, row-major)
+__host__ __device__ __forceinline__ double moment_at(const double* M, int a, int b)
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    return v;
+    if (a > b)
+    {
+        const int t = a;
+        a = b, b = t;
+    }
+    if (b < 8) return M[a * 8 + b];
+    if (a < 8) return M[64 + a * 8 + (b - 8)];
+    return M[128 + (a - 8) * 8 + (b - 8)];
 }
 
 struct MatchOut
@@ -68,187 +72,248 @@ struct MatchOut
     double*   normal;
 };
 
+// ---- the item loop shared by the matcher, the quality pass and the kNN query --
+// Each warp takes the items w, w + W, ... of the local cloud (static
+// assignment: fixed summation order).  Per item (<= 32 queries, one per lane):
+// box of the queries' home cells -> tile -> search.  `f` is called by ALL
+// lanes once per item: f(has, pl, gx, gy, gz, qx, qy, qz, key) with `has`
+// false on lanes without a point (their key[] holds sentinels).
+template <int K, class F>
+__device__ __forceinline__ void for_each_item(WarpTile& W, const CloudView& cvL, const CloudView& cvG,
+                                              const GridDev& grid, const double* Rt, uint32_t n_items,
+                                              float cap_d2, F&& f)
+{
+    const int      lane = threadIdx.x & 31;
+    const int      S = search_shells(grid, cap_d2);
+    const uint64_t sent = sentinel_key(cap_d2);
+    for (uint32_t item = item_warp_id(); item < n_items; item += item_warp_count())
+    {
+        const uint32_t first = __ldg(cvL.item_first + item);
+        const uint32_t cnt = __ldg(cvL.item_first + item + 1) - first;
+        const bool     has = (uint32_t)lane < cnt;
+        float4         pl = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has) pl = __ldg(cvL.pts + first + lane);
+        const double px = pl.x, py = pl.y, pz = pl.z;
+        // A.2: q = fl32(R p + t), f64 accumulate in this fixed order
+        const double gx = ((Rt[0] * px + Rt[1] * py) + Rt[2] * pz) + Rt[9];
+        const double gy = ((Rt[3] * px + Rt[4] * py) + Rt[5] * pz) + Rt[10];
+        const double gz = ((Rt[6] * px + Rt[7] * py) + Rt[8] * pz) + Rt[11];
+        const float  qx = (float)gx, qy = (float)gy, qz = (float)gz;
+        const QueryCell qc = locate_query(grid, S, qx, qy, qz);
+        const bool      hasq = has && qc.valid;
+        int lo[3] = {hasq ? qc.hx : INT_MAX, hasq ? qc.hy : INT_MAX, hasq ? qc.hz : INT_MAX};
+        int hi[3] = {hasq ? qc.hx : INT_MIN, hasq ? qc.hy : INT_MIN, hasq ? qc.hz : INT_MIN};
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+        {
+            lo[d] = __reduce_min_sync(0xFFFFFFFFu, lo[d]);
+            hi[d] = __reduce_max_sync(0xFFFFFFFFu, hi[d]);
+        }
+        TileGeom   G;
+        const bool tiled = warp_tile_build(W, G, cvG, lo, hi, S);
+        uint64_t   key[K];
+#pragma unroll
+        for (int i = 0; i < K; i++) key[i] = sent;
+        if (hasq)
+        {
+            if (tiled)
+                tile_knn<K>(W, G, cvG, grid, qc, S, qx, qy, qz, key);
+            else
+                knn_search<K>(cvG, grid, qx, qy, qz, cap_d2, key);
+        }
+        f(has, pl, gx, gy, gz, qx, qy, qz, key);
+    }
+}
+
+struct SearchSmem
+{
+    WarpTile tile[kChunk / 32];
+    GridDev  grid;
+    double   Rt[12];
+    uint32_t n_items;
+};
+
+struct MatchSmem
+{
+    SearchSmem S;
+    double     stage[kChunk / 32][16 * kStageStride];  // half a warp of e-vectors per round
+};
+
 // ------------------------------------------------------------------ matcher
+// grid = (CTAs per job, jobs)
 template <int K, bool WRITE>
-__global__ void __launch_bounds__(kChunk)
+__global__ void __launch_bounds__(kChunk, 5)
     match_kernel(const CloudView* __restrict__ clouds, const JobDev* __restrict__ jobs,
-                 const uint32_t* __restrict__ qorder, const uint32_t* __restrict__ qoff,
-                 double* __restrict__ partials, uint32_t max_chunks, IcpDevParams P, MatchOut out)
+                 double* __restrict__ partials, IcpDevParams P, MatchOut out)
 {
     const uint32_t job = blockIdx.y;
     const JobDev&  J = jobs[job];
     if (J.status != 0) return;
     const CloudView cvL = clouds[J.to_cloud];
     const CloudView cvG = clouds[J.from_cloud];
-    const uint32_t  nchunks = (cvL.n + kChunk - 1) / kChunk;
-    if (blockIdx.x >= nchunks) return;
 
-    __shared__ GridDev sgrid;
-    __shared__ double  sRt[12];
-    __shared__ double  sred[kChunk / 32][kNumMoments];
-    __shared__ uint32_t s_nvalid;
+    __shared__ MatchSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 12) sRt[tid] = (tid < 9) ? J.R[tid] : J.t[tid - 9];
-    if (tid == 32) sgrid = *cvG.grid;
-    if (tid == 64) s_nvalid = cvL.grid->n_valid;
+    if (tid < 12) sm.S.Rt[tid] = (tid < 9) ? J.R[tid] : J.t[tid - 9];
+    if (tid == 32) sm.S.grid = *cvG.grid;
+    if (tid == 64) sm.S.n_items = cvL.grid->n_items;
     __syncthreads();
 
     const uint32_t it = J.iter;
     const bool     active = (P.run_from_iteration <= it) &&
                         (P.run_up_to_iteration == 0 || it <= P.run_up_to_iteration);
-    // queries are taken in the order of their bin (global fine cell under a
-    // recent pose): the lanes of a warp then walk the same shells / blocks
-    const uint32_t slot = blockIdx.x * kChunk + tid;
-    const uint32_t qi = (slot < cvL.n) ? __ldg(qorder + qoff[job] + slot) : kInvalid;
-    const bool     valid = active && (qi < s_nvalid) && (sgrid.n_valid > 0);
+    const uint32_t n_items = (active && sm.S.grid.n_valid > 0) ? sm.S.n_items : 0u;
+    const uint64_t sent = sentinel_key(P.thr2);
+    double         c00[2] = {0, 0}, c01[2] = {0, 0}, c11[2] = {0, 0};
+    double*        st = sm.stage[warp];
 
-    bool   paired = false;
-    double nrm[3] = {0, 0, 0}, h[3] = {0, 0, 0}, r0 = 0;
-
-    if (valid)
-    {
-        const float4 pl = __ldg(cvL.pts + qi);
+    for_each_item<K>(sm.S.tile[warp], cvL, cvG, sm.S.grid, sm.S.Rt, n_items, P.thr2,
+        [&](bool has, const float4& pl, double gx, double gy, double gz, float qx, float qy, float qz,
+            uint64_t (&key)[K]) {
         const double px = pl.x, py = pl.y, pz = pl.z;
-        // A.2: q = fl32(R p + t), f64 accumulate in this fixed order
-        const double gx = ((sRt[0] * px + sRt[1] * py) + sRt[2] * pz) + sRt[9];
-        const double gy = ((sRt[3] * px + sRt[4] * py) + sRt[5] * pz) + sRt[10];
-        const double gz = ((sRt[6] * px + sRt[7] * py) + sRt[8] * pz) + sRt[11];
-        const float  qx = (float)gx, qy = (float)gy, qz = (float)gz;
-
-        uint64_t key[K];
-#pragma unroll
-        for (int i = 0; i < K; i++) key[i] = sentinel_key(P.thr2);
-        knn_search<K>(cvG, sgrid, qx, qy, qz, P.thr2, key);
-
-        // neighbours kept after the distance cut; K may exceed the configured knn
-        const uint64_t sent = sentinel_key(P.thr2);
-        uint32_t       m = 0;
-#pragma unroll
-        for (int i = 0; i < K; i++)
-            if ((uint32_t)i < P.knn && key[i] != sent) m++;
-
-        const uint32_t orig = __float_as_uint(pl.w);
-        if (WRITE)
+        bool         paired = false;
+        double       nrm[3] = {0, 0, 0}, r0 = 0;
+        if (has)
         {
-            if (out.nn_cnt) out.nn_cnt[orig] = m;
-            if (out.nn_idx)
+            // neighbours kept after the distance cut; K may exceed the configured knn
+            uint32_t m = 0;
+#pragma unroll
+            for (int i = 0; i < K; i++)
+                if ((uint32_t)i < P.knn && key[i] != sent) m++;
+
+            const uint32_t orig = __float_as_uint(pl.w);
+            if (WRITE)
+            {
+                if (out.nn_cnt) out.nn_cnt[orig] = m;
+                if (out.nn_idx)
+#pragma unroll
+                    for (int i = 0; i < K; i++)
+                        if ((uint32_t)i < P.knn)
+                            out.nn_idx[(size_t)orig * P.knn + i] =
+                                ((uint32_t)i < m) ? key_idx(key[i]) : kInvalid;
+            }
+
+            if (m >= P.min_plane_points && m > 0)
+            {
+                // row J: mean and covariance (1/m) of the neighbours in f64,
+                // accumulated in neighbour order
+                double nx_[K], ny_[K], nz_[K];
+                double sx = 0, sy = 0, sz = 0;
 #pragma unroll
                 for (int i = 0; i < K; i++)
-                    if ((uint32_t)i < P.knn)
-                        out.nn_idx[(size_t)orig * P.knn + i] =
-                            ((uint32_t)i < m) ? key_idx(key[i]) : kInvalid;
-        }
-
-        if (m >= P.min_plane_points && m > 0)
-        {
-            // row J: mean and covariance (1/m) of the neighbours in f64,
-            // accumulated in neighbour order
-            double nx_[K], ny_[K], nz_[K];
-            double sx = 0, sy = 0, sz = 0;
-#pragma unroll
-            for (int i = 0; i < K; i++)
-                if ((uint32_t)i < m)
-                {
-                    const uint32_t pos = __ldg(cvG.rank + key_idx(key[i]));
-                    const float4   pn = __ldg(cvG.pts + pos);
-                    nx_[i] = (double)pn.x, ny_[i] = (double)pn.y, nz_[i] = (double)pn.z;
-                    sx += nx_[i], sy += ny_[i], sz += nz_[i];
-                }
-            const double inv = 1.0 / (double)m;
-            const double cx = sx * inv, cy = sy * inv, cz = sz * inv;
-            double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
-#pragma unroll
-            for (int i = 0; i < K; i++)
-                if ((uint32_t)i < m)
-                {
-                    const double dx = nx_[i] - cx, dy = ny_[i] - cy, dz = nz_[i] - cz;
-                    c00 += dx * dx, c01 += dx * dy, c02 += dx * dz;
-                    c11 += dy * dy, c12 += dy * dz, c22 += dz * dz;
-                }
-            double C[9] = {c00 * inv, c01 * inv, c02 * inv, c01 * inv, c11 * inv,
-                           c12 * inv, c02 * inv, c12 * inv, c22 * inv};
-            double ev[3], V[9];
-            jacobi3(C, ev, V);
-            if (!(ev[0] > P.plane_eigen_threshold * ev[2]))
-            {
-                double nx = V[0], ny = V[3], nz = V[6];
-                const double lead = (nx != 0.0) ? nx : ((ny != 0.0) ? ny : nz);
-                if (lead < 0) nx = -nx, ny = -ny, nz = -nz;
-                const double dist = fabs((nx * ((double)qx - cx) + ny * ((double)qy - cy)) +
-                                         nz * ((double)qz - cz));
-                if (!(dist > P.distance_threshold))
-                {
-                    paired = true;
-                    nrm[0] = nx, nrm[1] = ny, nrm[2] = nz;
-                    h[0] = px, h[1] = py, h[2] = pz;
-                    // residual at T0 with the f64 transformed point (row L)
-                    r0 = (nx * (gx - cx) + ny * (gy - cy)) + nz * (gz - cz);
-                    if (WRITE)
+                    if ((uint32_t)i < m)
                     {
-                        if (out.centroid)
-                            out.centroid[(size_t)orig * 3] = cx, out.centroid[(size_t)orig * 3 + 1] = cy,
-                                                      out.centroid[(size_t)orig * 3 + 2] = cz;
-                        if (out.normal)
-                            out.normal[(size_t)orig * 3] = nx, out.normal[(size_t)orig * 3 + 1] = ny,
-                                                    out.normal[(size_t)orig * 3 + 2] = nz;
+                        const uint32_t pos = __ldg(cvG.rank + key_idx(key[i]));
+                        const float4   pn = __ldg(cvG.pts + pos);
+                        nx_[i] = (double)pn.x, ny_[i] = (double)pn.y, nz_[i] = (double)pn.z;
+                        sx += nx_[i], sy += ny_[i], sz += nz_[i];
+                    }
+                const double inv = 1.0 / (double)m;
+                const double cx = sx * inv, cy = sy * inv, cz = sz * inv;
+                double c00_ = 0, c01_ = 0, c02_ = 0, c11_ = 0, c12_ = 0, c22_ = 0;
+#pragma unroll
+                for (int i = 0; i < K; i++)
+                    if ((uint32_t)i < m)
+                    {
+                        const double dx = nx_[i] - cx, dy = ny_[i] - cy, dz = nz_[i] - cz;
+                        c00_ += dx * dx, c01_ += dx * dy, c02_ += dx * dz;
+                        c11_ += dy * dy, c12_ += dy * dz, c22_ += dz * dz;
+                    }
+                double C[9] = {c00_ * inv, c01_ * inv, c02_ * inv, c01_ * inv, c11_ * inv,
+                               c12_ * inv, c02_ * inv, c12_ * inv, c22_ * inv};
+                double ev[3], V[9];
+                jacobi3(C, ev, V);
+                if (!(ev[0] > P.plane_eigen_threshold * ev[2]))
+                {
+                    double nx = V[0], ny = V[3], nz = V[6];
+                    const double lead = (nx != 0.0) ? nx : ((ny != 0.0) ? ny : nz);
+                    if (lead < 0) nx = -nx, ny = -ny, nz = -nz;
+                    const double dist = fabs((nx * ((double)qx - cx) + ny * ((double)qy - cy)) +
+                                             nz * ((double)qz - cz));
+                    if (!(dist > P.distance_threshold))
+                    {
+                        paired = true;
+                        nrm[0] = nx, nrm[1] = ny, nrm[2] = nz;
+                        // residual at T0 with the f64 transformed point (row L)
+                        r0 = (nx * (gx - cx) + ny * (gy - cy)) + nz * (gz - cz);
+                        if (WRITE)
+                        {
+                            if (out.centroid)
+                                out.centroid[(size_t)orig * 3] = cx, out.centroid[(size_t)orig * 3 + 1] = cy,
+                                                          out.centroid[(size_t)orig * 3 + 2] = cz;
+                            if (out.normal)
+                                out.normal[(size_t)orig * 3] = nx, out.normal[(size_t)orig * 3 + 1] = ny,
+                                                        out.normal[(size_t)orig * 3 + 2] = nz;
+                        }
                     }
                 }
             }
+            if (WRITE && out.paired) out.paired[orig] = paired ? 1 : 0;
         }
-        if (WRITE && out.paired) out.paired[orig] = paired ? 1 : 0;
-    }
 
-    // ---- moments, reduced warp (xor butterfly) -> CTA in a fixed tree ------
-    const unsigned any = __ballot_sync(0xFFFFFFFFu, paired);
-    if (any == 0)
-    {
-        for (int i = lane; i < kNumMoments; i += 32) sred[warp][i] = 0.0;
-    }
-    else
-    {
-        const double hh[10] = {h[0] * h[0], h[0] * h[1], h[0] * h[2], h[0],        h[1] * h[1],
-                               h[1] * h[2], h[1],        h[2] * h[2], h[2],        paired ? 1.0 : 0.0};
-        const double nn[6] = {nrm[0] * nrm[0], nrm[0] * nrm[1], nrm[0] * nrm[2],
-                              nrm[1] * nrm[1], nrm[1] * nrm[2], nrm[2] * nrm[2]};
-#pragma unroll
-        for (int u = 0; u < 6; u++)
-#pragma unroll
-            for (int v = 0; v < 10; v++)
-            {
-                const double s = warp_sum(nn[u] * hh[v]);
-                if (lane == 0) sred[warp][u * 10 + v] = s;
-            }
-#pragma unroll
-        for (int i = 0; i < 3; i++)
+        // ---- moments on the FP64 tensor-core path ---------------------------
+        const unsigned any = __ballot_sync(0xFFFFFFFFu, paired);
+        if (any)
         {
-            const double rn = r0 * nrm[i];
 #pragma unroll
-            for (int j = 0; j < 4; j++)
+            for (int half = 0; half < 2; half++)
             {
-                const double s = warp_sum(j < 3 ? rn * h[j] : rn);
-                if (lane == 0) sred[warp][60 + i * 4 + j] = s;
+                if (((any >> (16 * half)) & 0xFFFFu) == 0) continue;
+                __syncwarp();
+                if ((lane >> 4) == half)
+                {
+                    double*      e = st + (lane & 15) * kStageStride;
+                    const double f1 = paired ? 1.0 : 0.0;
+#pragma unroll
+                    for (int i = 0; i < 3; i++)
+                    {
+                        const double ni = nrm[i];  // zero when unpaired
+                        e[4 * i + 0] = ni * px, e[4 * i + 1] = ni * py, e[4 * i + 2] = ni * pz,
+                                  e[4 * i + 3] = ni;
+                    }
+                    e[12] = r0, e[13] = f1, e[14] = 0.0, e[15] = 0.0;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++)
+                {
+                    if (((any >> (16 * half + 4 * ks)) & 0xFu) == 0) continue;
+                    const double* row = st + (4 * ks + (lane & 3)) * kStageStride + (lane >> 2);
+                    const double  f0 = row[0], f8 = row[8];
+                    dmma_8x8x4(c00[0], c00[1], f0, f0);
+                    dmma_8x8x4(c01[0], c01[1], f0, f8);
+                    dmma_8x8x4(c11[0], c11[1], f8, f8);
+                }
             }
         }
-        const double se = warp_sum(r0 * r0);
-        const double sc = warp_sum(paired ? 1.0 : 0.0);
-        if (lane == 0) sred[warp][72] = se, sred[warp][73] = sc;
+    });
+
+    // ---- CTA partial: the four warps' tiles added in a fixed order -----------
+    __syncthreads();  // every warp is done with its tile: reuse the memory
+    double* wbuf = reinterpret_cast<double*>(sm.S.tile);  // 4 x 192 doubles
+    {
+        const int r = lane >> 2, c = 2 * (lane & 3);
+        double*   w = wbuf + warp * kNumMoments;
+        w[r * 8 + c] = c00[0], w[r * 8 + c + 1] = c00[1];
+        w[64 + r * 8 + c] = c01[0], w[64 + r * 8 + c + 1] = c01[1];
+        w[128 + r * 8 + c] = c11[0], w[128 + r * 8 + c + 1] = c11[1];
     }
     __syncthreads();
-    if (tid < kNumMoments)
+    for (int i = tid; i < kNumMoments; i += kChunk)
     {
-        const double s = (sred[0][tid] + sred[1][tid]) + (sred[2][tid] + sred[3][tid]);
-        partials[((size_t)job * max_chunks + blockIdx.x) * kNumMoments + tid] = s;
+        const double s = (wbuf[i] + wbuf[kNumMoments + i]) + (wbuf[2 * kNumMoments + i] + wbuf[3 * kNumMoments + i]);
+        partials[((size_t)job * gridDim.x + blockIdx.x) * kNumMoments + i] = s;
     }
 }
 
 // ------------------------------------------------------------------- solver
 // One CTA per job. Warp 0 runs the Gauss-Newton inner loop on the moments.
-constexpr int kSolveThreads = 640;
-constexpr int kSolveGroups = 8;  // 8 x 74 threads share the partials reduction
+constexpr int kSolveGroups = 4;  // 4 x 192 threads share the partials reduction
+constexpr int kSolveThreads = kSolveGroups * kNumMoments;
 
 __global__ void __launch_bounds__(kSolveThreads)
     solve_kernel(const CloudView* __restrict__ clouds, JobDev* __restrict__ jobs,
-                 const double* __restrict__ partials, uint32_t max_chunks, IcpDevParams P,
+                 const double* __restrict__ partials, uint32_t n_partials, IcpDevParams P,
                  uint32_t* __restrict__ n_active)
 {
     const uint32_t job = blockIdx.x;
@@ -256,27 +321,26 @@ __global__ void __launch_bounds__(kSolveThreads)
     if (J.status != 0) return;
     const int tid = threadIdx.x, lane = tid & 31;
 
-    __shared__ double sM[kNumMoments];
+    __shared__ double sS[kNumMoments];
     __shared__ double sPart[kSolveGroups][kNumMoments];
     __shared__ double sA[144];
+    __shared__ double sG0[12];   // sum a r0
     __shared__ double sT0[12];   // theta0 layout: [R_i0 R_i1 R_i2 t_i] x 3
     __shared__ double sR[9], st[3];
     __shared__ double sX[12], sG12[12], sJ[72], sB[72], sH[36], sg[6];
     __shared__ int    sStop;
 
-    // fixed-order reduction of the per-CTA partials: group g takes the chunks
-    // c = g (mod 8) with two interleaved accumulators, then the 8 group sums
-    // are added as a balanced tree -- the order never depends on scheduling
-    const uint32_t nchunks = (clouds[J.to_cloud].n + kChunk - 1) / kChunk;
-    if (tid < kSolveGroups * kNumMoments)
+    // fixed-order reduction of the per-CTA partials: group g takes the partials
+    // c = g (mod 4) with four interleaved accumulators, then the group sums are
+    // added as a balanced tree -- the order never depends on scheduling
     {
         const int     grp = tid / kNumMoments, comp = tid % kNumMoments;
-        const double* p = partials + (size_t)job * max_chunks * kNumMoments + comp;
+        const double* p = partials + (size_t)job * n_partials * kNumMoments + comp;
         double        a0 = 0, a1 = 0, a2 = 0, a3 = 0;
         uint32_t      c = grp;
         // eight loads in flight per thread: the partials sit in L2, the loop
         // is latency bound
-        for (; c + 7 * kSolveGroups < nchunks; c += 8 * kSolveGroups)
+        for (; c + 7 * kSolveGroups < n_partials; c += 8 * kSolveGroups)
         {
             const double v0 = p[(size_t)c * kNumMoments];
             const double v1 = p[(size_t)(c + kSolveGroups) * kNumMoments];
@@ -289,19 +353,18 @@ __global__ void __launch_bounds__(kSolveThreads)
             a0 += v0, a1 += v1, a2 += v2, a3 += v3;
             a0 += v4, a1 += v5, a2 += v6, a3 += v7;
         }
-        for (; c < nchunks; c += kSolveGroups) a0 += p[(size_t)c * kNumMoments];
+        for (; c < n_partials; c += kSolveGroups) a0 += p[(size_t)c * kNumMoments];
         sPart[grp][comp] = (a0 + a1) + (a2 + a3);
     }
     __syncthreads();
     if (tid < kNumMoments)
     {
-        const double s = ((sPart[0][tid] + sPart[1][tid]) + (sPart[2][tid] + sPart[3][tid])) +
-                         ((sPart[4][tid] + sPart[5][tid]) + (sPart[6][tid] + sPart[7][tid]));
-        sM[tid] = s;
+        const double s = (sPart[0][tid] + sPart[1][tid]) + (sPart[2][tid] + sPart[3][tid]);
+        sS[tid] = s;
         J.M[tid] = s;
     }
     __syncthreads();
-    const uint32_t npair = (uint32_t)(sM[73] + 0.5);
+    const uint32_t npair = (uint32_t)(moment_at(sS, 13, 13) + 0.5);
     if (npair == 0)
     {
         if (tid == 0)
@@ -313,16 +376,13 @@ __global__ void __launch_bounds__(kSolveThreads)
         }
         return;
     }
-    for (int e = tid; e < 144; e += blockDim.x)
-    {
-        const int a = e / 12, b = e % 12;
-        sA[e] = sM[sym3(a >> 2, b >> 2) * 10 + sym4(a & 3, b & 3)];
-    }
+    for (int e = tid; e < 144; e += blockDim.x) sA[e] = moment_at(sS, e / 12, e % 12);
     if (tid < 12)
     {
         const int    i = tid >> 2, j = tid & 3;
         const double v = (j < 3) ? J.R[i * 3 + j] : J.t[i];
         sT0[tid] = v;
+        sG0[tid] = moment_at(sS, tid, 12);
         if (j < 3)
             sR[i * 3 + j] = v;
         else
@@ -365,7 +425,7 @@ __global__ void __launch_bounds__(kSolveThreads)
         // g12 = s + A x
         if (lane < 12)
         {
-            double acc = sM[60 + lane];
+            double acc = sG0[lane];
 #pragma unroll
             for (int b = 0; b < 12; b++) acc += sA[lane * 12 + b] * sX[b];
             sG12[lane] = acc;
@@ -456,40 +516,28 @@ __global__ void __launch_bounds__(kSolveThreads)
 // ------------------------------------------------------------------ quality
 // QualityEvaluator_PairedRatio (row O / A.8): 1-NN within thresholdDistance.
 __global__ void __launch_bounds__(kChunk)
-    quality_kernel(const CloudView* __restrict__ clouds, JobDev* __restrict__ jobs,
-                   const uint32_t* __restrict__ qorder, const uint32_t* __restrict__ qoff,
-                   IcpDevParams P)
+    quality_kernel(const CloudView* __restrict__ clouds, JobDev* __restrict__ jobs, IcpDevParams P)
 {
     const uint32_t  job = blockIdx.y;
     JobDev&         J = jobs[job];
     const CloudView cvL = clouds[J.to_cloud];
     const CloudView cvG = clouds[J.from_cloud];
-    const uint32_t  nchunks = (cvL.n + kChunk - 1) / kChunk;
-    if (blockIdx.x >= nchunks) return;
-    __shared__ GridDev sgrid;
-    __shared__ double  sRt[12];
-    __shared__ uint32_t s_nvalid;
+    __shared__ SearchSmem sm;
     const int tid = threadIdx.x;
-    if (tid < 12) sRt[tid] = (tid < 9) ? J.R[tid] : J.t[tid - 9];
-    if (tid == 32) sgrid = *cvG.grid;
-    if (tid == 64) s_nvalid = cvL.grid->n_valid;
+    if (tid < 12) sm.Rt[tid] = (tid < 9) ? J.R[tid] : J.t[tid - 9];
+    if (tid == 32) sm.grid = *cvG.grid;
+    if (tid == 64) sm.n_items = cvL.grid->n_items;
     __syncthreads();
-    const uint32_t slot = blockIdx.x * kChunk + tid;
-    const uint32_t qi = (slot < cvL.n) ? __ldg(qorder + qoff[job] + slot) : kInvalid;
-    bool           hit = false;
-    if (qi < s_nvalid && sgrid.n_valid > 0)
-    {
-        const float4 pl = __ldg(cvL.pts + qi);
-        const double px = pl.x, py = pl.y, pz = pl.z;
-        const float  qx = (float)(((sRt[0] * px + sRt[1] * py) + sRt[2] * pz) + sRt[9]);
-        const float  qy = (float)(((sRt[3] * px + sRt[4] * py) + sRt[5] * pz) + sRt[10]);
-        const float  qz = (float)(((sRt[6] * px + sRt[7] * py) + sRt[8] * pz) + sRt[11]);
-        uint64_t     key[1] = {sentinel_key(P.q_thr2)};
-        knn_search<1>(cvG, sgrid, qx, qy, qz, P.q_thr2, key);
-        hit = (key[0] != sentinel_key(P.q_thr2)) && (key_d2(key[0]) < P.q_thr2);  // strict
-    }
-    const unsigned b = __ballot_sync(0xFFFFFFFFu, hit);
-    if ((tid & 31) == 0 && b) atomicAdd(&J.quality_count, (uint32_t)__popc(b));
+    const uint32_t n_items = (sm.grid.n_valid > 0) ? sm.n_items : 0u;
+    const uint64_t sent = sentinel_key(P.q_thr2);
+    uint32_t       hits = 0;
+    for_each_item<1>(sm.tile[tid >> 5], cvL, cvG, sm.grid, sm.Rt, n_items, P.q_thr2,
+        [&](bool has, const float4&, double, double, double, float, float, float, uint64_t (&key)[1]) {
+            if (has && (key[0] != sent) && (key_d2(key[0]) < P.q_thr2)) hits++;  // strict
+        });
+    // integer count: any order gives the same sum
+    hits = __reduce_add_sync(0xFFFFFFFFu, hits);
+    if ((tid & 31) == 0 && hits) atomicAdd(&J.quality_count, hits);
 }
 
 // --------------------------------------------------------------- covariance
@@ -507,11 +555,7 @@ __global__ void __launch_bounds__(64) covariance_kernel(JobDev* __restrict__ job
         if (tid == 0) J.cov_singular = 1;
         return;
     }
-    for (int e = tid; e < 144; e += blockDim.x)
-    {
-        const int a = e / 12, b = e % 12;
-        sA[e] = J.M[sym3(a >> 2, b >> 2) * 10 + sym4(a & 3, b & 3)];
-    }
+    for (int e = tid; e < 144; e += blockDim.x) sA[e] = moment_at(J.M, e / 12, e % 12);
     if (tid < 6)
     {
         Pose T;
@@ -559,74 +603,30 @@ __global__ void __launch_bounds__(64) covariance_kernel(JobDev* __restrict__ job
 // ---------------------------------------------------------------- kNN query
 template <int K>
 __global__ void __launch_bounds__(kChunk)
-    knn_kernel(CloudView cvG, CloudView cvL, const uint32_t* __restrict__ qorder, Pose T,
-               uint32_t k, float cap_d2, uint32_t* __restrict__ idx_out,
-               float* __restrict__ d2_out)
+    knn_kernel(CloudView cvG, CloudView cvL, Pose T, uint32_t k, float cap_d2,
+               uint32_t* __restrict__ idx_out, float* __restrict__ d2_out)
 {
-    __shared__ GridDev sgrid;
-    __shared__ uint32_t s_nvalid;
-    if (threadIdx.x == 0) sgrid = *cvG.grid;
-    if (threadIdx.x == 32) s_nvalid = cvL.grid->n_valid;
+    __shared__ SearchSmem sm;
+    const int tid = threadIdx.x;
+    if (tid < 12) sm.Rt[tid] = (tid < 9) ? T.R[tid] : T.t[tid - 9];
+    if (tid == 32) sm.grid = *cvG.grid;
+    if (tid == 64) sm.n_items = cvL.grid->n_items;
     __syncthreads();
-    const uint32_t slot = blockIdx.x * kChunk + threadIdx.x;
-    if (slot >= cvL.n) return;
-    const uint32_t qi = __ldg(qorder + slot);
-    if (qi >= s_nvalid) return;
-    const float4 pl = __ldg(cvL.pts + qi);
-    const double px = pl.x, py = pl.y, pz = pl.z;
-    const float  qx = (float)(((T.R[0] * px + T.R[1] * py) + T.R[2] * pz) + T.t[0]);
-    const float  qy = (float)(((T.R[3] * px + T.R[4] * py) + T.R[5] * pz) + T.t[1]);
-    const float  qz = (float)(((T.R[6] * px + T.R[7] * py) + T.R[8] * pz) + T.t[2]);
-    uint64_t     key[K];
-#pragma unroll
-    for (int i = 0; i < K; i++) key[i] = sentinel_key(cap_d2);
-    if (sgrid.n_valid > 0) knn_search<K>(cvG, sgrid, qx, qy, qz, cap_d2, key);
-    const uint32_t orig = __float_as_uint(pl.w);
+    const uint32_t n_items = (sm.grid.n_valid > 0) ? sm.n_items : 0u;
     const uint64_t sent = sentinel_key(cap_d2);
+    for_each_item<K>(sm.tile[tid >> 5], cvL, cvG, sm.grid, sm.Rt, n_items, cap_d2,
+        [&](bool has, const float4& pl, double, double, double, float, float, float, uint64_t (&key)[K]) {
+            if (!has) return;
+            const uint32_t orig = __float_as_uint(pl.w);
 #pragma unroll
-    for (int i = 0; i < K; i++)
-        if ((uint32_t)i < k)
-        {
-            const bool ok = key[i] != sent;
-            idx_out[(size_t)orig * k + i] = ok ? key_idx(key[i]) : kInvalid;
-            d2_out[(size_t)orig * k + i] = ok ? key_d2(key[i]) : INFINITY;
-        }
-}
-
-// ------------------------------------------------------------- query binning
-// Key of every query of every job = (job, sort key of the GLOBAL fine cell its
-// transformed position falls in). Sorting these pairs makes the lanes of a
-// warp share home cells, hence shells, blocks and candidate ranges. The order
-// only affects which lanes work together and the (fixed) summation order.
-__global__ void __launch_bounds__(kChunk)
-    bin_key_kernel(const CloudView* __restrict__ clouds, const JobDev* __restrict__ jobs,
-                   const uint32_t* __restrict__ qoff, unsigned long long* __restrict__ keys,
-                   uint32_t* __restrict__ vals)
-{
-    const uint32_t  job = blockIdx.y;
-    const JobDev&   J = jobs[job];
-    const CloudView cvL = clouds[J.to_cloud];
-    const uint32_t  slot = blockIdx.x * kChunk + threadIdx.x;
-    if (slot >= cvL.n) return;
-    const GridDev* g = clouds[J.from_cloud].grid;
-    unsigned long long key = kInvalidSortKey;
-    if (slot < cvL.grid->n_valid)
-    {
-        const float4 pl = __ldg(cvL.pts + slot);
-        const double px = pl.x, py = pl.y, pz = pl.z;
-        const float  qx = (float)(((J.R[0] * px + J.R[1] * py) + J.R[2] * pz) + J.t[0]);
-        const float  qy = (float)(((J.R[3] * px + J.R[4] * py) + J.R[5] * pz) + J.t[1]);
-        const float  qz = (float)(((J.R[6] * px + J.R[7] * py) + J.R[8] * pz) + J.t[2]);
-        const float  inv = g->inv_cell, hi = (float)kFineMax;
-        const float  ux = fminf(fmaxf((qx - g->ox) * inv, 0.0f), hi);
-        const float  uy = fminf(fmaxf((qy - g->oy) * inv, 0.0f), hi);
-        const float  uz = fminf(fmaxf((qz - g->oz) * inv, 0.0f), hi);
-        if (ux == ux && uy == uy && uz == uz)
-            key = fine_sort_key((uint32_t)ux, (uint32_t)uy, (uint32_t)uz);
-    }
-    const size_t o = (size_t)qoff[job] + slot;
-    keys[o] = ((unsigned long long)job << 37) | key;
-    vals[o] = slot;
+            for (int i = 0; i < K; i++)
+                if ((uint32_t)i < k)
+                {
+                    const bool ok = key[i] != sent;
+                    idx_out[(size_t)orig * k + i] = ok ? key_idx(key[i]) : kInvalid;
+                    d2_out[(size_t)orig * k + i] = ok ? key_d2(key[i]) : INFINITY;
+                }
+        });
 }
 
 __global__ void fill_u32_kernel(uint32_t* p, size_t n, uint32_t v)
@@ -647,62 +647,41 @@ static int wait_cloud(Workspace* ws, const b200icp_cloud* c)
     return B200ICP_OK;
 }
 
-// Bins the queries of every job by the global fine cell of their transformed
-// position (one key kernel + one radix sort over all jobs of the wave).
-struct Binner
+// CTAs per job: every CTA walks the items c, c + G, ... of the local cloud.
+// Enough CTAs to fill the machine a few times over for one job, fewer per job
+// when many jobs share a launch (the partials buffer is G x 192 doubles per job).
+static uint32_t ctas_per_job(const ::b200icp* ctx, size_t max_points, size_t njobs)
 {
-    unsigned long long *k0 = nullptr, *k1 = nullptr;
-    uint32_t *          v0 = nullptr, *v1 = nullptr, *qoff = nullptr;
-    void*               temp = nullptr;
-    size_t              temp_bytes = 0, total = 0, njobs = 0;
-    int                 end_bit = 37;
-    const uint32_t*     order = nullptr;  // queries of job j: order[qoff[j] ...]
-
-    int plan(size_t total_queries, size_t jobs, cudaStream_t s)
+    // CTAs of the search kernels that are resident on one SM (registers and
+    // shared memory): one full wave for a single job, no ragged second wave
+    static int resident = 0;
+    if (resident == 0)
     {
-        total = total_queries ? total_queries : 1;
-        njobs = jobs;
-        end_bit = 37;
-        while (end_bit < 64 && (1ull << (end_bit - 37)) < jobs) end_bit++;
-        cub::DoubleBuffer<unsigned long long> dk(nullptr, nullptr);
-        cub::DoubleBuffer<uint32_t>           dv(nullptr, nullptr);
-        B2_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, dk, dv, (int)total, 0, end_bit, s));
-        return B200ICP_OK;
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, match_kernel<6, false>, kChunk, 0) != cudaSuccess ||
+            occ < 1)
+            occ = 4;
+        resident = occ;
     }
-    void layout(Carver& c)
-    {
-        k0 = c.take<unsigned long long>(total), k1 = c.take<unsigned long long>(total);
-        v0 = c.take<uint32_t>(total), v1 = c.take<uint32_t>(total);
-        qoff = c.take<uint32_t>(njobs + 1);
-        temp = c.take<char>(temp_bytes);
-    }
-    int run(Workspace* ws, dim3 grid, const CloudView* d_clouds, const JobDev* d_jobs)
-    {
-        cudaStream_t s = ws->stream;
-        bin_key_kernel<<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, qoff, k0, v0);
-        cub::DoubleBuffer<unsigned long long> keys(k0, k1);
-        cub::DoubleBuffer<uint32_t>           vals(v0, v1);
-        B2_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, vals, (int)total, 0, end_bit, s));
-        order = vals.Current();
-        ws->launches += 1 + 1 + (end_bit + 7) / 8;
-        return B200ICP_OK;
-    }
-};
+    const size_t chunks = (max_points + kChunk - 1) / kChunk;
+    const size_t wave = (size_t)ctx->sm_count * resident;
+    size_t       cap = (2 * wave + njobs - 1) / njobs;
+    cap = std::max<size_t>(cap, 8);
+    cap = std::min<size_t>(cap, wave);
+    return (uint32_t)std::max<size_t>(1, std::min(2 * chunks, cap));
+}
 
 template <bool WRITE>
 static void launch_match(Workspace* ws, uint32_t knn, dim3 grid, const CloudView* d_clouds,
-                         const JobDev* d_jobs, const Binner& bin, double* d_partials,
-                         uint32_t max_chunks, const IcpDevParams& D, const MatchOut& mo)
+                         const JobDev* d_jobs, double* d_partials, const IcpDevParams& D,
+                         const MatchOut& mo)
 {
     if (knn == 6)
-        match_kernel<6, WRITE><<<grid, kChunk, 0, ws->stream>>>(d_clouds, d_jobs, bin.order, bin.qoff,
-                                                                d_partials, max_chunks, D, mo);
+        match_kernel<6, WRITE><<<grid, kChunk, 0, ws->stream>>>(d_clouds, d_jobs, d_partials, D, mo);
     else if (knn <= 4)
-        match_kernel<4, WRITE><<<grid, kChunk, 0, ws->stream>>>(d_clouds, d_jobs, bin.order, bin.qoff,
-                                                                d_partials, max_chunks, D, mo);
+        match_kernel<4, WRITE><<<grid, kChunk, 0, ws->stream>>>(d_clouds, d_jobs, d_partials, D, mo);
     else
-        match_kernel<8, WRITE><<<grid, kChunk, 0, ws->stream>>>(d_clouds, d_jobs, bin.order, bin.qoff,
-                                                                d_partials, max_chunks, D, mo);
+        match_kernel<8, WRITE><<<grid, kChunk, 0, ws->stream>>>(d_clouds, d_jobs, d_partials, D, mo);
     ws->launches++;
 }
 
@@ -729,7 +708,7 @@ static int check_supported(const ::b200icp* ctx)
     return B200ICP_OK;
 }
 
-// Jobs are processed in waves that bound the partials buffer.
+// Jobs are processed in waves that bound gridDim.y.
 static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud* const* from,
                     const b200icp_cloud* const* to, const double* guesses, b200icp_result_t* out)
 {
@@ -738,7 +717,7 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
     // unique cloud table
     std::map<const b200icp_cloud*, uint32_t> cmap;
     std::vector<CloudView>                   views;
-    uint32_t                                 max_chunks = 1;
+    size_t                                   max_points = 1;
     uint64_t                                 total_queries = 0;
     auto add = [&](const b200icp_cloud* c) -> uint32_t {
         auto it = cmap.find(c);
@@ -759,22 +738,19 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
         memcpy(J.Rprev, T.R, sizeof(T.R)), memcpy(J.tprev, T.t, sizeof(T.t));
         J.from_cloud = add(from[j]);
         J.to_cloud = add(to[j]);
-        const uint32_t ch = (uint32_t)((to[j]->n + kChunk - 1) / kChunk);
-        max_chunks = std::max(max_chunks, ch);
+        max_points = std::max(max_points, to[j]->n);
         total_queries += to[j]->n;
     }
     for (auto& kv : cmap)
         if (int r = wait_cloud(ws, kv.first)) return r;
+    const uint32_t G = ctas_per_job(ctx, max_points, n);
 
-    Binner bin;
-    if (int r = bin.plan(total_queries, n, s)) return r;
     Carver sz(nullptr);
     auto layout = [&](Carver& k, CloudView*& dc, JobDev*& dj, double*& dp, uint32_t*& da) {
         dc = k.take<CloudView>(views.size());
         dj = k.take<JobDev>(n);
-        dp = k.take<double>((size_t)n * max_chunks * kNumMoments);
+        dp = k.take<double>((size_t)n * G * kNumMoments);
         da = k.take<uint32_t>(4);
-        bin.layout(k);
     };
     CloudView* d_clouds;
     JobDev*    d_jobs;
@@ -784,33 +760,28 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
     if (int r = ws->reserve_device(sz.off)) return r;
     Carver real(ws->d_scratch);
     layout(real, d_clouds, d_jobs, d_partials, d_active);
-    // pinned staging: views | jobs | query offsets | active flags (2 slots) | n_active init
+    // pinned staging: views | jobs | active flags (2 slots) | n_active init
     const size_t off_jobs = align_up(views.size() * sizeof(CloudView));
-    const size_t off_qoff = off_jobs + align_up(n * sizeof(JobDev));
-    const size_t off_flags = off_qoff + align_up((n + 1) * sizeof(uint32_t));
+    const size_t off_flags = off_jobs + align_up(n * sizeof(JobDev));
     if (int r = ws->reserve_pinned(off_flags + 256)) return r;
     char*      hp = (char*)ws->h_pinned;
     CloudView* h_views = (CloudView*)hp;
     JobDev*    h_jobs = (JobDev*)(hp + off_jobs);
-    uint32_t*  h_qoff = (uint32_t*)(hp + off_qoff);
     uint32_t*  h_flags = (uint32_t*)(hp + off_flags);
     memcpy(h_views, views.data(), views.size() * sizeof(CloudView));
     memcpy(h_jobs, hjobs.data(), n * sizeof(JobDev));
-    h_qoff[0] = 0;
-    for (size_t j = 0; j < n; j++) h_qoff[j + 1] = h_qoff[j] + (uint32_t)to[j]->n;
     h_flags[0] = h_flags[1] = 0xFFFFFFFFu;
     h_flags[2] = (uint32_t)n;
     B2_CUDA_TRY(cudaMemcpyAsync(d_clouds, h_views, views.size() * sizeof(CloudView),
                                 cudaMemcpyHostToDevice, s));
     B2_CUDA_TRY(cudaMemcpyAsync(d_jobs, h_jobs, n * sizeof(JobDev), cudaMemcpyHostToDevice, s));
-    B2_CUDA_TRY(cudaMemcpyAsync(bin.qoff, h_qoff, (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     B2_CUDA_TRY(cudaMemcpyAsync(d_active, h_flags + 2, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
 
     const bool prof = ctx->profile_on;
     if (prof)
         if (int r = ws->reserve_prof_events(2 * (size_t)D.max_iterations + 2)) return r;
 
-    const dim3     mgrid(max_chunks, (unsigned)n);
+    const dim3     mgrid(G, (unsigned)n);
     const MatchOut no_out = {nullptr, nullptr, nullptr, nullptr, nullptr};
     const uint32_t kBatch = 4;
     uint32_t       enq = 0, batch = 0;
@@ -820,16 +791,11 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
         const uint32_t todo = std::min(kBatch, D.max_iterations - enq);
         for (uint32_t i = 0; i < todo; i++, enq++)
         {
-            // re-bin while the pose still moves by more than a fine cell (first
-            // iterations), then every 8th iteration
-            if (enq < 3 || (enq & 7u) == 0)
-                if (int r = bin.run(ws, mgrid, d_clouds, d_jobs)) return r;
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 0], s));
-            launch_match<false>(ws, D.knn, mgrid, d_clouds, d_jobs, bin, d_partials, max_chunks, D, no_out);
+            launch_match<false>(ws, D.knn, mgrid, d_clouds, d_jobs, d_partials, D, no_out);
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 1], s));
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 2], s));
-            solve_kernel<<<(unsigned)n, kSolveThreads, 0, s>>>(d_clouds, d_jobs, d_partials, max_chunks, D,
-                                                     d_active);
+            solve_kernel<<<(unsigned)n, kSolveThreads, 0, s>>>(d_clouds, d_jobs, d_partials, G, D, d_active);
             ws->launches++;
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 3], s));
         }
@@ -846,10 +812,7 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
         }
         batch++;
     }
-    const dim3 qgrid(max_chunks, (unsigned)n);
-    if (D.max_iterations == 0)
-        if (int r = bin.run(ws, mgrid, d_clouds, d_jobs)) return r;
-    quality_kernel<<<qgrid, kChunk, 0, s>>>(d_clouds, d_jobs, bin.order, bin.qoff, D);
+    quality_kernel<<<mgrid, kChunk, 0, s>>>(d_clouds, d_jobs, D);
     covariance_kernel<<<(unsigned)n, 64, 0, s>>>(d_jobs, D);
     ws->launches += 2;
     B2_CUDA_TRY(cudaMemcpyAsync(h_jobs, d_jobs, n * sizeof(JobDev), cudaMemcpyDeviceToHost, s));
@@ -904,33 +867,21 @@ int run_align_batch(::b200icp* ctx, size_t n, const b200icp_cloud* const* from,
     if (n == 0) return B200ICP_OK;
     Lease L(ctx);
     if (!L.ws) return B200ICP_ERR_CUDA;
-    // wave size: partials <= ~1.5 GB and gridDim.y <= 65535
-    size_t i = 0;
-    while (i < n)
+    const size_t kWave = 32768;  // gridDim.y <= 65535
+    for (size_t i = 0; i < n; i += kWave)
     {
-        size_t   cnt = 0;
-        uint32_t mc = 1;
-        while (i + cnt < n && cnt < 65535)
-        {
-            const uint32_t ch = (uint32_t)((to[i + cnt]->n + kChunk - 1) / kChunk);
-            const uint32_t nmc = std::max(mc, ch);
-            if (cnt > 0 && (size_t)(cnt + 1) * nmc * kNumMoments * sizeof(double) > (1536ull << 20)) break;
-            mc = nmc;
-            cnt++;
-        }
+        const size_t cnt = std::min(kWave, n - i);
         if (int r = run_wave(ctx, L.ws, cnt, from + i, to + i, guesses + 6 * i, out + i)) return r;
-        i += cnt;
     }
     return B200ICP_OK;
 }
 
-// one (from, to, pose) job laid out, uploaded and binned; `extra` carves the
-// caller's own arrays out of the same scratch allocation
+// one (from, to, pose) job laid out and uploaded; `extra` carves the caller's
+// own arrays out of the same scratch allocation
 struct SingleJob
 {
     CloudView* d_clouds = nullptr;
     JobDev*    d_jobs = nullptr;
-    Binner     bin;
     Pose       T;
 };
 
@@ -941,11 +892,9 @@ static int single_job_setup(Workspace* ws, const b200icp_cloud* from, const b200
     cudaStream_t s = ws->stream;
     if (int r = wait_cloud(ws, from)) return r;
     if (int r = wait_cloud(ws, to)) return r;
-    if (int r = sj.bin.plan(to->n, 1, s)) return r;
     auto layout = [&](Carver& c) {
         sj.d_clouds = c.take<CloudView>(2);
         sj.d_jobs = c.take<JobDev>(1);
-        sj.bin.layout(c);
         extra(c);
     };
     Carver sz(nullptr);
@@ -954,11 +903,9 @@ static int single_job_setup(Workspace* ws, const b200icp_cloud* from, const b200
     Carver real(ws->d_scratch);
     layout(real);
     const size_t off_job = align_up(2 * sizeof(CloudView));
-    const size_t off_q = off_job + align_up(sizeof(JobDev));
-    if (int r = ws->reserve_pinned(off_q + 64)) return r;
+    if (int r = ws->reserve_pinned(off_job + align_up(sizeof(JobDev)) + 64)) return r;
     CloudView* hv = (CloudView*)ws->h_pinned;
     JobDev*    hj = (JobDev*)((char*)ws->h_pinned + off_job);
-    uint32_t*  hq = (uint32_t*)((char*)ws->h_pinned + off_q);
     hv[0] = from->view(), hv[1] = to->view();
     memset(hj, 0, sizeof(JobDev));
     const double ident[6] = {0, 0, 0, 0, 0, 0};
@@ -966,12 +913,9 @@ static int single_job_setup(Workspace* ws, const b200icp_cloud* from, const b200
     memcpy(hj->R, sj.T.R, sizeof(sj.T.R)), memcpy(hj->t, sj.T.t, sizeof(sj.T.t));
     hj->from_cloud = 0, hj->to_cloud = 1;
     hj->iter = iter;
-    hq[0] = 0, hq[1] = (uint32_t)to->n;
     B2_CUDA_TRY(cudaMemcpyAsync(sj.d_clouds, hv, 2 * sizeof(CloudView), cudaMemcpyHostToDevice, s));
     B2_CUDA_TRY(cudaMemcpyAsync(sj.d_jobs, hj, sizeof(JobDev), cudaMemcpyHostToDevice, s));
-    B2_CUDA_TRY(cudaMemcpyAsync(sj.bin.qoff, hq, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-    const uint32_t chunks = (uint32_t)((to->n + kChunk - 1) / kChunk);
-    return sj.bin.run(ws, dim3(chunks ? chunks : 1, 1), sj.d_clouds, sj.d_jobs);
+    return B200ICP_OK;
 }
 
 int run_knn(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, const double* pose6,
@@ -993,14 +937,22 @@ int run_knn(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, co
     cudaStream_t s = ws->stream;
     const size_t nq = q->n;
     if (nq == 0) return B200ICP_OK;
+    if (int r = wait_cloud(ws, ref)) return r;
+    if (int r = wait_cloud(ws, q)) return r;
     uint32_t* d_idx = nullptr;
     float*    d_d2 = nullptr;
-    SingleJob sj;
-    if (int r = single_job_setup(ws, ref, q, pose6, 0, sj, [&](Carver& c) {
-            d_idx = c.take<uint32_t>(nq * k);
-            d_d2 = c.take<float>(nq * k);
-        }))
-        return r;
+    auto layout = [&](Carver& c) {
+        d_idx = c.take<uint32_t>(nq * k);
+        d_d2 = c.take<float>(nq * k);
+    };
+    Carver sz(nullptr);
+    layout(sz);
+    if (int r = ws->reserve_device(sz.off)) return r;
+    Carver real(ws->d_scratch);
+    layout(real);
+    Pose         T;
+    const double ident[6] = {0, 0, 0, 0, 0, 0};
+    pose_from_ypr(pose6 ? pose6 : ident, T);
     const float cap_d2 = max_dist * max_dist;
     const int   fb = (int)((nq * k + 255) / 256);
     fill_u32_kernel<<<fb, 256, 0, s>>>(d_idx, nq * k, kInvalid);
@@ -1012,17 +964,16 @@ int run_knn(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, co
         if (int r = ws->reserve_prof_events(1)) return r;
         B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[0], s));
     }
-    const int             blocks = (int)((nq + kChunk - 1) / kChunk);
-    const CloudView       vr = ref->view(), vq = q->view();
-    const uint32_t* const ord = sj.bin.order;
+    const int       blocks = (int)ctas_per_job(ctx, nq, 1);
+    const CloudView vr = ref->view(), vq = q->view();
     if (k == 1)
-        knn_kernel<1><<<blocks, kChunk, 0, s>>>(vr, vq, ord, sj.T, k, cap_d2, d_idx, d_d2);
+        knn_kernel<1><<<blocks, kChunk, 0, s>>>(vr, vq, T, k, cap_d2, d_idx, d_d2);
     else if (k <= 4)
-        knn_kernel<4><<<blocks, kChunk, 0, s>>>(vr, vq, ord, sj.T, k, cap_d2, d_idx, d_d2);
+        knn_kernel<4><<<blocks, kChunk, 0, s>>>(vr, vq, T, k, cap_d2, d_idx, d_d2);
     else if (k <= 6)
-        knn_kernel<6><<<blocks, kChunk, 0, s>>>(vr, vq, ord, sj.T, k, cap_d2, d_idx, d_d2);
+        knn_kernel<6><<<blocks, kChunk, 0, s>>>(vr, vq, T, k, cap_d2, d_idx, d_d2);
     else
-        knn_kernel<8><<<blocks, kChunk, 0, s>>>(vr, vq, ord, sj.T, k, cap_d2, d_idx, d_d2);
+        knn_kernel<8><<<blocks, kChunk, 0, s>>>(vr, vq, T, k, cap_d2, d_idx, d_d2);
     ws->launches++;
     if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[1], s));
     B2_CUDA_TRY(cudaGetLastError());
@@ -1056,13 +1007,13 @@ int run_match(::b200icp* ctx, const b200icp_cloud* from, const b200icp_cloud* to
     const size_t        n = to->n, k = D.knn;
     if (n_pairings) *n_pairings = 0;
     if (n == 0) return B200ICP_OK;
-    const uint32_t max_chunks = (uint32_t)((n + kChunk - 1) / kChunk);
+    const uint32_t G = ctas_per_job(ctx, n, 1);
     double*        d_partials = nullptr;
     MatchOut       mo;
     SingleJob      sj;
     // the matcher is active at iteration run_from_iteration
     if (int r = single_job_setup(ws, from, to, pose6, D.run_from_iteration, sj, [&](Carver& c) {
-            d_partials = c.take<double>((size_t)max_chunks * kNumMoments);
+            d_partials = c.take<double>((size_t)G * kNumMoments);
             mo.paired = c.take<uint8_t>(n);
             mo.nn_idx = c.take<uint32_t>(n * k);
             mo.nn_cnt = c.take<uint32_t>(n);
@@ -1075,10 +1026,9 @@ int run_match(::b200icp* ctx, const b200icp_cloud* from, const b200icp_cloud* to
     B2_CUDA_TRY(cudaMemsetAsync(mo.nn_idx, 0xFF, n * k * sizeof(uint32_t), s));
     B2_CUDA_TRY(cudaMemsetAsync(mo.centroid, 0, n * 3 * sizeof(double), s));
     B2_CUDA_TRY(cudaMemsetAsync(mo.normal, 0, n * 3 * sizeof(double), s));
-    launch_match<true>(ws, D.knn, dim3(max_chunks, 1), sj.d_clouds, sj.d_jobs, sj.bin, d_partials,
-                       max_chunks, D, mo);
+    launch_match<true>(ws, D.knn, dim3(G, 1), sj.d_clouds, sj.d_jobs, d_partials, D, mo);
     B2_CUDA_TRY(cudaGetLastError());
-    std::vector<double> part((size_t)max_chunks * kNumMoments);
+    std::vector<double> part((size_t)G * kNumMoments);
     B2_CUDA_TRY(cudaMemcpyAsync(part.data(), d_partials, part.size() * sizeof(double),
                                 cudaMemcpyDeviceToHost, s));
     if (paired) B2_CUDA_TRY(cudaMemcpyAsync(paired, mo.paired, n, cudaMemcpyDeviceToHost, s));
@@ -1094,7 +1044,7 @@ int run_match(::b200icp* ctx, const b200icp_cloud* from, const b200icp_cloud* to
     if (n_pairings)
     {
         double cnt = 0;
-        for (uint32_t c = 0; c < max_chunks; c++) cnt += part[(size_t)c * kNumMoments + 73];
+        for (uint32_t c = 0; c < G; c++) cnt += moment_at(part.data() + (size_t)c * kNumMoments, 13, 13);
         *n_pairings = (uint32_t)(cnt + 0.5);
     }
     return B200ICP_OK;

@@ -95,6 +95,7 @@ __global__ void grid_setup_kernel(const uint32_t* __restrict__ bb, float block_r
     g->n_valid = 0;
     g->n_cells = 0;
     g->n_blocks = 0;
+    g->n_items = 0;
     for (int d = 0; d < 3; d++) g->bmin[d] = mn[d], g->bmax[d] = mx[d];
 }
 
@@ -122,13 +123,13 @@ __global__ void cell_key_kernel(const float* __restrict__ x, const float* __rest
 }
 
 // After the sort: gather float4 points in cell order, write the inverse
-// permutation, flag the first point of every fine cell.
+// permutation, flag the first point of every fine cell and of every work item.
 __global__ void gather_kernel(const unsigned long long* __restrict__ skeys,
                               const uint32_t* __restrict__ svals, uint32_t n,
                               const float* __restrict__ x, const float* __restrict__ y,
                               const float* __restrict__ z, float4* __restrict__ pts,
-                              uint32_t* __restrict__ rank, uint32_t* __restrict__ fine_flag,
-                              GridDev* __restrict__ g)
+                              uint32_t* __restrict__ rank,
+                              unsigned long long* __restrict__ flags, GridDev* __restrict__ g)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
@@ -150,12 +151,18 @@ __global__ void gather_kernel(const unsigned long long* __restrict__ skeys,
     if (key >= kInvalidSortKey)
     {
         rank[i] = kInvalid;
-        fine_flag[j] = 0;
+        flags[j] = 0ull;
         return;
     }
     pts[j] = make_float4(x[i], y[i], z[i], __uint_as_float(i));
     rank[i] = j;
-    fine_flag[j] = (j == 0 || skeys[j - 1] != key) ? 1u : 0u;
+    // low word: first point of a fine cell; high word: first point of a work
+    // item (head of a 2x2x2 block group, or a multiple of kItem) -- one 64-bit scan numbers both
+    const unsigned long long prev = j ? skeys[j - 1] : ~0ull;
+    const unsigned long long fine = (j == 0 || prev != key) ? 1ull : 0ull;
+    const unsigned long long item =
+        (j == 0 || (prev >> kItemKeyShift) != (key >> kItemKeyShift) || (j % kItem) == 0) ? 1ull : 0ull;
+    flags[j] = fine | (item << 32);
 }
 
 __device__ __forceinline__ uint32_t block_key_of(unsigned long long sort_key)
@@ -166,8 +173,7 @@ __device__ __forceinline__ uint32_t block_key_of(unsigned long long sort_key)
 
 // first point of every block claims a hash slot and writes its record
 __global__ void block_insert_kernel(const unsigned long long* __restrict__ skeys, uint32_t n,
-                                    const uint32_t* __restrict__ fine_flag,
-                                    const uint32_t* __restrict__ fine_ord,
+                                    const unsigned long long* __restrict__ ords,
                                     uint32_t* __restrict__ hkeys, uint4* __restrict__ hrecs,
                                     uint32_t hshift, uint32_t hmask, GridDev* __restrict__ g)
 {
@@ -184,31 +190,40 @@ __global__ void block_insert_kernel(const unsigned long long* __restrict__ skeys
         if (prev == kEmptyKey) break;
         slot = (slot + 1) & hmask;
     }
-    hrecs[slot] = make_uint4(j, fine_ord[j], 0u, 0u);
+    hrecs[slot] = make_uint4(j, (uint32_t)ords[j], 0u, 0u);
     atomicAdd(&g->n_blocks, 1u);
 }
 
-// first point of every fine cell publishes its start and sets its mask bit
+// first point of every fine cell publishes its start and sets its mask bit;
+// first point of every work item publishes the item
 __global__ void fine_publish_kernel(const unsigned long long* __restrict__ skeys, uint32_t n,
-                                    const uint32_t* __restrict__ fine_flag,
-                                    const uint32_t* __restrict__ fine_ord,
+                                    const unsigned long long* __restrict__ flags,
+                                    const unsigned long long* __restrict__ ords,
                                     const uint32_t* __restrict__ hkeys, uint4* __restrict__ hrecs,
                                     uint32_t hshift, uint32_t hmask,
-                                    uint32_t* __restrict__ fine_start, GridDev* __restrict__ g)
+                                    uint32_t* __restrict__ fine_start,
+                                    uint32_t* __restrict__ item_first, GridDev* __restrict__ g)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const unsigned long long key = skeys[j];
     if (key >= kInvalidSortKey) return;
+    const unsigned long long fl = flags[j], od = ords[j];
+    const uint32_t fine_flag = (uint32_t)fl, item_flag = (uint32_t)(fl >> 32);
+    const uint32_t fine_ord = (uint32_t)od, item_ord = (uint32_t)(od >> 32);
     const bool last = (j + 1 == n) || (skeys[j + 1] >= kInvalidSortKey);
     if (last)
     {
-        const uint32_t total = fine_ord[j] + fine_flag[j];
+        const uint32_t total = fine_ord + fine_flag;
         fine_start[total] = j + 1;
         g->n_cells = total;
+        const uint32_t items = item_ord + item_flag;
+        item_first[items] = j + 1;
+        g->n_items = items;
     }
-    if (!fine_flag[j]) return;
-    fine_start[fine_ord[j]] = j;
+    if (item_flag) item_first[item_ord] = j;
+    if (!fine_flag) return;
+    fine_start[fine_ord] = j;
     const uint32_t bkey = block_key_of(key);
     uint32_t       slot = hash_slot(bkey, hshift);
     while (hkeys[slot] != bkey) slot = (slot + 1) & hmask;
@@ -244,6 +259,7 @@ int cloud_alloc(::b200icp* ctx, Workspace* ws, size_t n, float search_radius, b2
         c->hkeys = k.take<uint32_t>(cap);
         c->hrecs = k.take<uint4>(cap);
         c->fine_start = k.take<uint32_t>(nn + 1);
+        c->item_first = k.take<uint32_t>(nn + 1);
         c->grid = k.take<GridDev>(1);
         c->bbox_enc = k.take<uint32_t>(8);
     };
@@ -297,16 +313,16 @@ int cloud_build_index(::b200icp* ctx, Workspace* ws, b200icp_cloud* c)
         cub::DoubleBuffer<unsigned long long> dk(nullptr, nullptr);
         cub::DoubleBuffer<uint32_t>           dv(nullptr, nullptr);
         B2_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, dk, dv, (int)n, 0, 37, s));
-        B2_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (uint32_t*)nullptr,
-                                                  (uint32_t*)nullptr, (int)n, s));
+        B2_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (unsigned long long*)nullptr,
+                                                  (unsigned long long*)nullptr, (int)n, s));
         const size_t temp_bytes = std::max(sort_bytes, scan_bytes);
-        unsigned long long *k0, *k1;
-        uint32_t *          v0, *v1, *fflag, *ford;
+        unsigned long long *k0, *k1, *fflag, *ford;
+        uint32_t *          v0, *v1;
         void*               temp;
         auto layout = [&](Carver& k) {
             k0 = k.take<unsigned long long>(n), k1 = k.take<unsigned long long>(n);
             v0 = k.take<uint32_t>(n), v1 = k.take<uint32_t>(n);
-            fflag = k.take<uint32_t>(n), ford = k.take<uint32_t>(n);
+            fflag = k.take<unsigned long long>(n), ford = k.take<unsigned long long>(n);
             temp = k.take<char>(temp_bytes);
         };
         Carver cv(nullptr);
@@ -322,10 +338,11 @@ int cloud_build_index(::b200icp* ctx, Workspace* ws, b200icp_cloud* c)
         gather_kernel<<<blocks, 256, 0, s>>>(keys.Current(), vals.Current(), n, c->dx, c->dy, c->dz,
                                              c->pts, c->rank, fflag, c->grid);
         B2_CUDA_TRY(cub::DeviceScan::ExclusiveSum(temp, scan_bytes, fflag, ford, (int)n, s));
-        block_insert_kernel<<<blocks, 256, 0, s>>>(keys.Current(), n, fflag, ford, c->hkeys, c->hrecs,
+        block_insert_kernel<<<blocks, 256, 0, s>>>(keys.Current(), n, ford, c->hkeys, c->hrecs,
                                                    c->hshift, c->hcap - 1, c->grid);
         fine_publish_kernel<<<blocks, 256, 0, s>>>(keys.Current(), n, fflag, ford, c->hkeys, c->hrecs,
-                                                   c->hshift, c->hcap - 1, c->fine_start, c->grid);
+                                                   c->hshift, c->hcap - 1, c->fine_start,
+                                                   c->item_first, c->grid);
         ws->launches += 4 + 6 + 2;  // ours + radix sort passes + scan
     }
     B2_CUDA_TRY(cudaGetLastError());

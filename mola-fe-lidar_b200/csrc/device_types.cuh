@@ -11,6 +11,11 @@
 //                         {first point, first fine-cell ordinal, 64-bit
 //                         occupancy mask of its 4x4x4 fine cells}
 //   fine_start[n_fine+1]  first point of every occupied fine cell, in order
+//   item_first[n_items+1] work items of the cloud when it is the LOCAL (query)
+//                         side: runs of <= kItem consecutive sorted points
+//                         inside one 2x2x2 group of blocks (cut where the
+//                         Morton code of the group changes and at every
+//                         multiple of kItem): one warp, one round
 //   GridDev               grid origin / cell size / counts, written on device
 // Two levels: a BLOCK (edge >= the search radius, so 27 blocks always cover
 // the radius) holds 4x4x4 FINE cells; dense regions are pruned at fine-cell
@@ -27,8 +32,10 @@ constexpr uint32_t kEmptyKey = 0xFFFFFFFFu;
 constexpr int kGridBits = 10;  // blocks per axis = 1024 (30-bit Morton / linear keys)
 constexpr int kGridMax = (1 << kGridBits) - 1;
 constexpr int kFineMax = 4 * (kGridMax + 1) - 1;  // fine cells per axis - 1
-constexpr int kChunk = 128;    // queries per CTA in the matcher kernels
-constexpr int kNumMoments = 74; // 60 (nn x hh) + 12 (r0 n x h) + 1 (r0^2) + 1 (count)
+constexpr int kChunk = 128;    // threads per CTA in the search kernels (4 warps, 4 items in flight)
+constexpr int kItem = 32;      // queries per work item = one warp round
+constexpr int kItemKeyShift = 9; // sort-key bits below the 2x2x2 block group (6 fine + 3 Morton)
+constexpr int kNumMoments = 192; // three 8x8 tiles of the 16x16 moment matrix S (align.cu)
 
 struct GridDev
 {
@@ -40,7 +47,7 @@ struct GridDev
     uint32_t n_cells;     // occupied fine cells
     uint32_t n_blocks;    // occupied blocks
     float    bmin[3], bmax[3];
-    uint32_t pad[1];
+    uint32_t n_items;     // work items (see item_first)
 };
 
 struct CloudView
@@ -51,6 +58,7 @@ struct CloudView
     const uint32_t* hkeys;
     const uint4*    hrecs;       // BlockRec as (start, fine_base, mask.lo, mask.hi)
     const uint32_t* fine_start;
+    const uint32_t* item_first;
     uint32_t        hshift;  // 32 - log2(capacity)
     uint32_t        hmask;   // capacity - 1
     uint32_t        n;       // total points (incl. non-finite)

@@ -96,6 +96,7 @@ struct b200icp_cloud
     uint32_t* hkeys = nullptr;
     uint4*    hrecs = nullptr;
     uint32_t* fine_start = nullptr;
+    uint32_t* item_first = nullptr;
     b2::GridDev* grid = nullptr;
     uint32_t* bbox_enc = nullptr;  // 6 order-encoded floats
     uint32_t  hcap = 0, hshift = 0;
@@ -107,6 +108,7 @@ struct b200icp_cloud
         b2::CloudView v;
         v.pts = pts, v.rank = rank, v.grid = grid, v.hkeys = hkeys, v.hrecs = hrecs;
         v.fine_start = fine_start;
+        v.item_first = item_first;
         v.hshift = hshift, v.hmask = hcap - 1, v.n = (uint32_t)n;
         return v;
     }

@@ -81,8 +81,11 @@ def test_batch_equals_single(icp, oracle, rng):
     batch = icp.align_batch(froms, tos, guesses)
     for i in range(6):
         single = icp.align(froms[i], tos[i], guesses[i])
-        for key in ("pose", "cov"):
-            assert np.array_equal(batch[i][key], single[key]), key
+        # the number of CTAs per job (hence the fixed summation order of the
+        # moment partials) depends on how many jobs share a launch: same
+        # correspondences, sums equal to rounding
+        assert np.abs(batch[i]["pose"] - single["pose"]).max() < 1e-9
+        assert np.allclose(batch[i]["cov"], single["cov"], rtol=1e-6, atol=1e-12)
         for key in ("quality", "n_iterations", "termination_reason", "n_pairings"):
             assert batch[i][key] == single[key], key
     o = oracle.icp_align(oracle.Cloud(A), oracle.Cloud(B), guesses[0], oracle.default_params())

@@ -96,7 +96,9 @@ def test_scan_to_scan_flow_matches_oracle(oracle, voxel):
         assert st["last_icp_termination"] == r["termination_reason"]
     lo.wait_idle()
     st = lo.state()
-    assert st["n_keyframes"] == len(kfs) >= 2
+    # decimated scans score a low PairedRatio (0.10 m gate on 0.5 m voxels): the
+    # key-frame rule then only fires for the first scan, on both sides
+    assert st["n_keyframes"] == len(kfs) >= (2 if voxel is None else 1)
     assert np.abs(st["accum_since_last_kf"][:3] - accum[:3]).max() < 5e-5
     assert np.abs(st["last_twist"][[0, 1, 2, 5]] - twist).max() < 1e-3
     assert st["last_iter_twist_is_good"] == 1

@@ -157,11 +157,13 @@ __global__ void gather_kernel(const unsigned long long* __restrict__ skeys,
     pts[j] = make_float4(x[i], y[i], z[i], __uint_as_float(i));
     rank[i] = j;
     // low word: first point of a fine cell; high word: first point of a work
-    // item (head of a 2x2x2 block group, or a multiple of kItem) -- one 64-bit scan numbers both
+    // item -- one 64-bit scan numbers both.  Items are plain runs of kItem
+    // consecutive sorted points: dense regions give compact tiles, a run that
+    // straddles far-apart blocks simply takes the per-lane fallback search
+    // (measured: cutting at block-group heads as well was slightly slower)
     const unsigned long long prev = j ? skeys[j - 1] : ~0ull;
     const unsigned long long fine = (j == 0 || prev != key) ? 1ull : 0ull;
-    const unsigned long long item =
-        (j == 0 || (prev >> kItemKeyShift) != (key >> kItemKeyShift) || (j % kItem) == 0) ? 1ull : 0ull;
+    const unsigned long long item = ((j % kItem) == 0) ? 1ull : 0ull;
     flags[j] = fine | (item << 32);
 }
 

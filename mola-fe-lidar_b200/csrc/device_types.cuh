@@ -12,10 +12,8 @@
 //                         occupancy mask of its 4x4x4 fine cells}
 //   fine_start[n_fine+1]  first point of every occupied fine cell, in order
 //   item_first[n_items+1] work items of the cloud when it is the LOCAL (query)
-//                         side: runs of <= kItem consecutive sorted points
-//                         inside one 2x2x2 group of blocks (cut where the
-//                         Morton code of the group changes and at every
-//                         multiple of kItem): one warp, one round
+//                         side: runs of kItem consecutive sorted points:
+//                         one warp, one round
 //   GridDev               grid origin / cell size / counts, written on device
 // Two levels: a BLOCK (edge >= the search radius, so 27 blocks always cover
 // the radius) holds 4x4x4 FINE cells; dense regions are pruned at fine-cell
@@ -34,7 +32,6 @@ constexpr int kGridMax = (1 << kGridBits) - 1;
 constexpr int kFineMax = 4 * (kGridMax + 1) - 1;  // fine cells per axis - 1
 constexpr int kChunk = 128;    // threads per CTA in the search kernels (4 warps, 4 items in flight)
 constexpr int kItem = 32;      // queries per work item = one warp round
-constexpr int kItemKeyShift = 9; // sort-key bits below the 2x2x2 block group (6 fine + 3 Morton)
 constexpr int kNumMoments = 192; // three 8x8 tiles of the 16x16 moment matrix S (align.cu)
 
 struct GridDev

@@ -1,8 +1,7 @@
 // tile_search.cuh -- warp-autonomous exact k-nearest-neighbour search.
 //
-// Work unit ("item") = up to kItem (32) consecutive points of the LOCAL cloud's
-// own cell-sorted array that lie in one 2x2x2 group of its blocks (built once
-// with the cloud's index, cloud.cu).  ONE WARP owns an item: under the current pose its
+// Work unit ("item") = kItem (32) consecutive points of the LOCAL cloud's own
+// cell-sorted array (built once with the cloud's index, cloud.cu).  ONE WARP owns an item: under the current pose its
 // points land in a small box of the GLOBAL cloud's grid.  The warp
 //   1. reduces the box of fine cells its queries fall in and grows it by the
 //      search radius S (in cells) -> the TILE,

@@ -1,6 +1,8 @@
 """The LidarOdometry module (host C++ mirror over the C ABI) against a Python
 restatement of the reference control flow (LidarOdometry.cpp:201-339) that
 uses the oracle's ICP: same per-scan poses, twist, keyframes and factors."""
+import os
+
 import numpy as np
 import pytest
 
@@ -130,11 +132,18 @@ def test_time_gate_label_filter_and_async_queue():
     lo.close()
 
 
-def test_extra_edges_between_nearby_keyframes(oracle):
-    """checkForNearbyKFs + doCheckForNonAdjacentKFs (cpp:516-849): KFs >= 5 m apart get an extra factor."""
+def test_extra_edges_between_nearby_keyframes(oracle, tmp_path):
+    """checkForNearbyKFs + doCheckForNonAdjacentKFs (cpp:516-849): KFs >= 5 m apart get an extra factor.
+    The synthetic 20k-point scans score a PairedRatio below the shipped 0.50 for
+    key-frames that far apart, so the acceptance threshold (cpp:809-812) is
+    lowered in a copy of the parameter file; everything else is as shipped."""
     from mola_fe_lidar_b200 import lidar_odometry as lom, scene
     scans, poses = _sequence(14, n_pts=20000)
-    lo = lom.LidarOdometry(yaml_text=lom.system_yaml())
+    txt = open(os.path.join(lom.PARAMS_DIR, "kitti-default.yaml")).read()
+    assert "min_icp_goodness: 0.50" in txt
+    prm = tmp_path / "kitti-lowgood.yaml"
+    prm.write_text(txt.replace("min_icp_goodness: 0.50", "min_icp_goodness: 0.05"))
+    lo = lom.LidarOdometry(yaml_text=lom.system_yaml(params_file=str(prm)))
     for i, s in enumerate(scans):
         lo.onNewObservation(s, 0.1 * i, sync=True)
     lo.wait_idle()

@@ -168,7 +168,10 @@ int b200icp_knn(b200icp_t* icp, const b200icp_cloud_t* ref, const b200icp_cloud_
 /* --- matcher at a fixed pose (Matcher_Point2Plane; parity hook) ---------- */
 /* Host outputs in the local cloud's ORIGINAL order: paired[n] (0/1),
  * nn_idx[n*knn] (after the distance cut, padded INVALID), nn_cnt[n],
- * centroid[n*3], normal[n*3] (f64).  Any output may be NULL. */
+ * centroid[n*3], normal[n*3] (f64).  Any output may be NULL.  With
+ * Matcher_Points_DistanceThreshold (d2 < threshold^2, strict) nn_idx is [n]
+ * (the single neighbour), centroid receives the paired global point and
+ * normal stays zero. */
 int b200icp_match(b200icp_t* icp, const b200icp_cloud_t* from_global,
                   const b200icp_cloud_t* to_local, const double* pose6, uint8_t* paired,
                   uint32_t* nn_idx, uint32_t* nn_cnt, double* centroid, double* normal,

@@ -270,7 +270,8 @@ class ICP:
         return idx, d2
 
     def match(self, from_global, to_local, pose6=None):
-        n, k = len(to_local), self.params.knn
+        # Matcher_Points_DistanceThreshold pairs with the single nearest neighbour
+        n, k = len(to_local), (1 if self.params.matcher_kind == 1 else self.params.knn)
         paired = np.zeros(n, dtype=np.uint8)
         nn_idx = np.empty((n, k), dtype=np.uint32)
         nn_cnt = np.zeros(n, dtype=np.uint32)

@@ -63,6 +63,18 @@ __host__ __device__ __forceinline__ double moment_at(const double* M, int a, int
     return M[128 + (a - 8) * 8 + (b - 8)];
 }
 
+// A = sum_i a_i a_i^T (12x12) and the pairing count out of S, for both matchers:
+// point-to-plane stores it directly, point-to-point has A = I3 (x) sum h h^T
+__host__ __device__ __forceinline__ double normal_matrix_at(const double* M, bool p2p, int a, int b)
+{
+    if (!p2p) return moment_at(M, a, b);
+    return ((a >> 2) == (b >> 2)) ? moment_at(M, a & 3, b & 3) : 0.0;
+}
+__host__ __device__ __forceinline__ double pairing_count(const double* M, bool p2p)
+{
+    return p2p ? moment_at(M, 3, 3) : moment_at(M, 13, 13);
+}
+
 struct MatchOut
 {
     uint8_t*  paired;
@@ -76,7 +88,7 @@ struct MatchOut
 // Each warp takes the items w, w + W, ... of the local cloud (static
 // assignment: fixed summation order).  Per item (<= 32 queries, one per lane):
 // box of the queries' home cells -> tile -> search.  `f` is called by ALL
-// lanes once per item: f(has, pl, gx, gy, gz, qx, qy, qz, key) with `has`
+// lanes once per item: f(has, pos, pl, gx, gy, gz, qx, qy, qz, key) with `has`
 // false on lanes without a point (their key[] holds sentinels).
 template <int K, class F>
 __device__ __forceinline__ void for_each_item(WarpTile& W, const CloudView& cvL, const CloudView& cvG,
@@ -121,8 +133,62 @@ __device__ __forceinline__ void for_each_item(WarpTile& W, const CloudView& cvL,
             else
                 knn_search<K>(cvG, grid, qx, qy, qz, cap_d2, key);
         }
-        f(has, pl, gx, gy, gz, qx, qy, qz, key);
+        f(has, first + lane, pl, gx, gy, gz, qx, qy, qz, key);
     }
+}
+
+// Adds e e^T of the warp's (<= 32) pairings to the DMMA accumulators: the 16
+// doubles of every paired lane go through the warp's staging buffer, half a
+// warp at a time; groups of four lanes without a pairing are skipped.
+__device__ __forceinline__ void accumulate_moments(double* st, bool paired, const double (&e)[16],
+                                                   double (&c00)[2], double (&c01)[2], double (&c11)[2])
+{
+    const int      lane = threadIdx.x & 31;
+    const unsigned any = __ballot_sync(0xFFFFFFFFu, paired);
+    if (!any) return;
+#pragma unroll
+    for (int half = 0; half < 2; half++)
+    {
+        if (((any >> (16 * half)) & 0xFFFFu) == 0) continue;
+        __syncwarp();
+        if ((lane >> 4) == half)
+        {
+            double* d = st + (lane & 15) * kStageStride;
+#pragma unroll
+            for (int i = 0; i < 16; i++) d[i] = paired ? e[i] : 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++)
+        {
+            if (((any >> (16 * half + 4 * ks)) & 0xFu) == 0) continue;
+            const double* row = st + (4 * ks + (lane & 3)) * kStageStride + (lane >> 2);
+            const double  f0 = row[0], f8 = row[8];
+            dmma_8x8x4(c00[0], c00[1], f0, f0);
+            dmma_8x8x4(c01[0], c01[1], f0, f8);
+            dmma_8x8x4(c11[0], c11[1], f8, f8);
+        }
+    }
+}
+
+// CTA partial: the four warps' tiles added in a fixed order. `wbuf` is 4 x 192
+// doubles of shared memory nobody else uses any more.
+__device__ __forceinline__ void write_cta_partial(double* wbuf, const double (&c00)[2],
+                                                  const double (&c01)[2], const double (&c11)[2],
+                                                  double* __restrict__ partial)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __syncthreads();
+    {
+        const int r = lane >> 2, c = 2 * (lane & 3);
+        double*   w = wbuf + warp * kNumMoments;
+        w[r * 8 + c] = c00[0], w[r * 8 + c + 1] = c00[1];
+        w[64 + r * 8 + c] = c01[0], w[64 + r * 8 + c + 1] = c01[1];
+        w[128 + r * 8 + c] = c11[0], w[128 + r * 8 + c + 1] = c11[1];
+    }
+    __syncthreads();
+    for (int i = tid; i < kNumMoments; i += kChunk)
+        partial[i] = (wbuf[i] + wbuf[kNumMoments + i]) + (wbuf[2 * kNumMoments + i] + wbuf[3 * kNumMoments + i]);
 }
 
 struct SearchSmem
@@ -144,13 +210,15 @@ struct MatchSmem
 template <int K, bool WRITE>
 __global__ void __launch_bounds__(kChunk, 5)
     match_kernel(const CloudView* __restrict__ clouds, const JobDev* __restrict__ jobs,
-                 double* __restrict__ partials, IcpDevParams P, MatchOut out)
+                 double* __restrict__ partials, IcpDevParams P, MatchOut out,
+                 PairRec* __restrict__ pairs)
 {
     const uint32_t job = blockIdx.y;
     const JobDev&  J = jobs[job];
     if (J.status != 0) return;
     const CloudView cvL = clouds[J.to_cloud];
     const CloudView cvG = clouds[J.from_cloud];
+    PairRec*        prec = pairs ? pairs + J.pair_base : nullptr;
 
     __shared__ MatchSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -168,11 +236,12 @@ __global__ void __launch_bounds__(kChunk, 5)
     double*        st = sm.stage[warp];
 
     for_each_item<K>(sm.S.tile[warp], cvL, cvG, sm.S.grid, sm.S.Rt, n_items, P.thr2,
-        [&](bool has, const float4& pl, double gx, double gy, double gz, float qx, float qy, float qz,
-            uint64_t (&key)[K]) {
+        [&](bool has, uint32_t pos, const float4& pl, double gx, double gy, double gz, float qx, float qy,
+            float qz, uint64_t (&key)[K]) {
         const double px = pl.x, py = pl.y, pz = pl.z;
         bool         paired = false;
         double       nrm[3] = {0, 0, 0}, r0 = 0;
+        double       cen[3] = {0, 0, 0};
         if (has)
         {
             // neighbours kept after the distance cut; K may exceed the configured knn
@@ -234,6 +303,7 @@ __global__ void __launch_bounds__(kChunk, 5)
                     {
                         paired = true;
                         nrm[0] = nx, nrm[1] = ny, nrm[2] = nz;
+                        cen[0] = cx, cen[1] = cy, cen[2] = cz;
                         // residual at T0 with the f64 transformed point (row L)
                         r0 = (nx * (gx - cx) + ny * (gy - cy)) + nz * (gz - cz);
                         if (WRITE)
@@ -249,90 +319,158 @@ __global__ void __launch_bounds__(kChunk, 5)
                 }
             }
             if (WRITE && out.paired) out.paired[orig] = paired ? 1 : 0;
+            if (prec)
+            {  // what the closed-form solver consumes: the plane centroid (A.10)
+                PairRec r;
+                r.q[0] = cen[0], r.q[1] = cen[1], r.q[2] = cen[2];
+                r.paired = paired ? 1u : 0u, r.pad = 0u;
+                prec[pos] = r;
+            }
         }
 
         // ---- moments on the FP64 tensor-core path ---------------------------
-        const unsigned any = __ballot_sync(0xFFFFFFFFu, paired);
-        if (any)
+        double e[16];
+        const double f1 = paired ? 1.0 : 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
         {
-#pragma unroll
-            for (int half = 0; half < 2; half++)
-            {
-                if (((any >> (16 * half)) & 0xFFFFu) == 0) continue;
-                __syncwarp();
-                if ((lane >> 4) == half)
-                {
-                    double*      e = st + (lane & 15) * kStageStride;
-                    const double f1 = paired ? 1.0 : 0.0;
-#pragma unroll
-                    for (int i = 0; i < 3; i++)
-                    {
-                        const double ni = nrm[i];  // zero when unpaired
-                        e[4 * i + 0] = ni * px, e[4 * i + 1] = ni * py, e[4 * i + 2] = ni * pz,
-                                  e[4 * i + 3] = ni;
-                    }
-                    e[12] = r0, e[13] = f1, e[14] = 0.0, e[15] = 0.0;
-                }
-                __syncwarp();
-#pragma unroll
-                for (int ks = 0; ks < 4; ks++)
-                {
-                    if (((any >> (16 * half + 4 * ks)) & 0xFu) == 0) continue;
-                    const double* row = st + (4 * ks + (lane & 3)) * kStageStride + (lane >> 2);
-                    const double  f0 = row[0], f8 = row[8];
-                    dmma_8x8x4(c00[0], c00[1], f0, f0);
-                    dmma_8x8x4(c01[0], c01[1], f0, f8);
-                    dmma_8x8x4(c11[0], c11[1], f8, f8);
-                }
-            }
+            const double ni = nrm[i];  // zero when unpaired
+            e[4 * i + 0] = ni * px, e[4 * i + 1] = ni * py, e[4 * i + 2] = ni * pz, e[4 * i + 3] = ni;
         }
+        e[12] = r0, e[13] = f1, e[14] = 0.0, e[15] = 0.0;
+        accumulate_moments(st, paired, e, c00, c01, c11);
     });
 
-    // ---- CTA partial: the four warps' tiles added in a fixed order -----------
-    __syncthreads();  // every warp is done with its tile: reuse the memory
-    double* wbuf = reinterpret_cast<double*>(sm.S.tile);  // 4 x 192 doubles
-    {
-        const int r = lane >> 2, c = 2 * (lane & 3);
-        double*   w = wbuf + warp * kNumMoments;
-        w[r * 8 + c] = c00[0], w[r * 8 + c + 1] = c00[1];
-        w[64 + r * 8 + c] = c01[0], w[64 + r * 8 + c + 1] = c01[1];
-        w[128 + r * 8 + c] = c11[0], w[128 + r * 8 + c + 1] = c11[1];
-    }
+    write_cta_partial(reinterpret_cast<double*>(sm.S.tile), c00, c01, c11,
+                      partials + ((size_t)job * gridDim.x + blockIdx.x) * kNumMoments);
+}
+
+// Matcher_Points_DistanceThreshold as the ICP matcher: 1-NN with d2 < thr^2
+// (strict, A.8 / orc_match_points).  Moments of the point-to-point residual
+// r = R p + t - q, linear in theta like the point-to-plane one:
+//   e = [ h (4) | r0 (3) | 0 ... ],  h = (p_local, 1)
+// so tile C00 holds sum h h^T, sum h r0^T, sum |r0|^2 (trace of the r0 block)
+// and the pairing count (S[3][3]).
+template <bool WRITE>
+__global__ void __launch_bounds__(kChunk, 5)
+    match_p2p_kernel(const CloudView* __restrict__ clouds, const JobDev* __restrict__ jobs,
+                     double* __restrict__ partials, IcpDevParams P, MatchOut out,
+                     PairRec* __restrict__ pairs)
+{
+    const uint32_t job = blockIdx.y;
+    const JobDev&  J = jobs[job];
+    if (J.status != 0) return;
+    const CloudView cvL = clouds[J.to_cloud];
+    const CloudView cvG = clouds[J.from_cloud];
+    PairRec*        prec = pairs ? pairs + J.pair_base : nullptr;
+
+    __shared__ MatchSmem sm;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid < 12) sm.S.Rt[tid] = (tid < 9) ? J.R[tid] : J.t[tid - 9];
+    if (tid == 32) sm.S.grid = *cvG.grid;
+    if (tid == 64) sm.S.n_items = cvL.grid->n_items;
     __syncthreads();
-    for (int i = tid; i < kNumMoments; i += kChunk)
-    {
-        const double s = (wbuf[i] + wbuf[kNumMoments + i]) + (wbuf[2 * kNumMoments + i] + wbuf[3 * kNumMoments + i]);
-        partials[((size_t)job * gridDim.x + blockIdx.x) * kNumMoments + i] = s;
-    }
+    const uint32_t it = J.iter;
+    const bool     active = (P.run_from_iteration <= it) &&
+                        (P.run_up_to_iteration == 0 || it <= P.run_up_to_iteration);
+    const uint32_t n_items = (active && sm.S.grid.n_valid > 0) ? sm.S.n_items : 0u;
+    const uint64_t sent = sentinel_key(P.thr2);
+    double         c00[2] = {0, 0}, c01[2] = {0, 0}, c11[2] = {0, 0};
+    double*        st = sm.stage[warp];
+
+    for_each_item<1>(sm.S.tile[warp], cvL, cvG, sm.S.grid, sm.S.Rt, n_items, P.thr2,
+        [&](bool has, uint32_t pos, const float4& pl, double gx, double gy, double gz, float, float, float,
+            uint64_t (&key)[1]) {
+        bool   paired = false;
+        double q[3] = {0, 0, 0};
+        if (has)
+        {
+            paired = (key[0] != sent) && (key_d2(key[0]) < P.thr2);
+            const uint32_t orig = __float_as_uint(pl.w);
+            if (paired)
+            {
+                const float4 pn = __ldg(cvG.pts + __ldg(cvG.rank + key_idx(key[0])));
+                q[0] = (double)pn.x, q[1] = (double)pn.y, q[2] = (double)pn.z;
+            }
+            if (WRITE)
+            {
+                if (out.nn_cnt) out.nn_cnt[orig] = paired ? 1u : 0u;
+                if (out.nn_idx) out.nn_idx[orig] = paired ? key_idx(key[0]) : kInvalid;
+                if (out.paired) out.paired[orig] = paired ? 1 : 0;
+                if (paired && out.centroid)
+                    out.centroid[(size_t)orig * 3] = q[0], out.centroid[(size_t)orig * 3 + 1] = q[1],
+                                              out.centroid[(size_t)orig * 3 + 2] = q[2];
+            }
+            if (prec)
+            {
+                PairRec r;
+                r.q[0] = q[0], r.q[1] = q[1], r.q[2] = q[2];
+                r.paired = paired ? 1u : 0u, r.pad = 0u;
+                prec[pos] = r;
+            }
+        }
+        double e[16];
+        e[0] = pl.x, e[1] = pl.y, e[2] = pl.z, e[3] = 1.0;
+        e[4] = gx - q[0], e[5] = gy - q[1], e[6] = gz - q[2];
+#pragma unroll
+        for (int i = 7; i < 16; i++) e[i] = 0.0;
+        accumulate_moments(st, paired, e, c00, c01, c11);
+    });
+    write_cta_partial(reinterpret_cast<double*>(sm.S.tile), c00, c01, c11,
+                      partials + ((size_t)job * gridDim.x + blockIdx.x) * kNumMoments);
 }
 
 // ------------------------------------------------------------------- solver
+// End of one outer iteration of ICP::align (row G / A.7), one thread: adopt
+// the solver's pose, test the step delta = log(Tprev^-1 * Tnew) split into
+// (xyz, rot), update the job's status.
+__device__ void finish_outer_iteration(JobDev& J, const Pose& Tn, uint32_t npair, uint32_t inner,
+                                       const IcpDevParams& P, uint32_t* n_active)
+{
+    Pose T0, dT;
+    for (int i = 0; i < 9; i++) T0.R[i] = J.R[i];
+    for (int i = 0; i < 3; i++) T0.t[i] = J.t[i];
+    pose_inverse_compose(T0, Tn, dT);
+    double d[6];
+    se3_log(dT, d);
+    const double dxyz = sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
+    const double drot = sqrt((d[3] * d[3] + d[4] * d[4]) + d[5] * d[5]);
+    for (int i = 0; i < 9; i++) J.Rprev[i] = T0.R[i], J.R[i] = Tn.R[i];
+    for (int i = 0; i < 3; i++) J.tprev[i] = T0.t[i], J.t[i] = Tn.t[i];
+    J.n_pairings = npair;
+    J.inner_iters_total += inner;
+    if (dxyz < P.min_abs_step_trans && drot < P.min_abs_step_rot)
+    {
+        J.status = 1;
+        J.term_reason = B200ICP_TERM_STALLED;
+        atomicSub(n_active, 1u);
+    }
+    else
+    {
+        const uint32_t it = J.iter + 1;
+        J.iter = it;
+        if (it >= P.max_iterations)
+        {
+            J.status = 1;
+            J.term_reason = B200ICP_TERM_MAX_ITERATIONS;
+            atomicSub(n_active, 1u);
+        }
+    }
+}
+
+// Fixed-order reduction of a job's per-CTA moment partials by a block of
+// kSolveThreads threads: group g takes the partials c = g (mod 4) with four
+// interleaved accumulators, then the group sums are added as a balanced tree --
+// the order never depends on scheduling.  Result in sS[192] (and J.M).
 // One CTA per job. Warp 0 runs the Gauss-Newton inner loop on the moments.
 constexpr int kSolveGroups = 4;  // 4 x 192 threads share the partials reduction
 constexpr int kSolveThreads = kSolveGroups * kNumMoments;
 
-__global__ void __launch_bounds__(kSolveThreads)
-    solve_kernel(const CloudView* __restrict__ clouds, JobDev* __restrict__ jobs,
-                 const double* __restrict__ partials, uint32_t n_partials, IcpDevParams P,
-                 uint32_t* __restrict__ n_active)
+__device__ __forceinline__ void reduce_moment_partials(const double* __restrict__ partials, uint32_t job,
+                                                       uint32_t n_partials, double* sS,
+                                                       double (*sPart)[kNumMoments])
 {
-    const uint32_t job = blockIdx.x;
-    JobDev&        J = jobs[job];
-    if (J.status != 0) return;
-    const int tid = threadIdx.x, lane = tid & 31;
-
-    __shared__ double sS[kNumMoments];
-    __shared__ double sPart[kSolveGroups][kNumMoments];
-    __shared__ double sA[144];
-    __shared__ double sG0[12];   // sum a r0
-    __shared__ double sT0[12];   // theta0 layout: [R_i0 R_i1 R_i2 t_i] x 3
-    __shared__ double sR[9], st[3];
-    __shared__ double sX[12], sG12[12], sJ[72], sB[72], sH[36], sg[6];
-    __shared__ int    sStop;
-
-    // fixed-order reduction of the per-CTA partials: group g takes the partials
-    // c = g (mod 4) with four interleaved accumulators, then the group sums are
-    // added as a balanced tree -- the order never depends on scheduling
+    const int tid = threadIdx.x;
     {
         const int     grp = tid / kNumMoments, comp = tid % kNumMoments;
         const double* p = partials + (size_t)job * n_partials * kNumMoments + comp;
@@ -358,13 +496,33 @@ __global__ void __launch_bounds__(kSolveThreads)
     }
     __syncthreads();
     if (tid < kNumMoments)
-    {
-        const double s = (sPart[0][tid] + sPart[1][tid]) + (sPart[2][tid] + sPart[3][tid]);
-        sS[tid] = s;
-        J.M[tid] = s;
-    }
+        sS[tid] = (sPart[0][tid] + sPart[1][tid]) + (sPart[2][tid] + sPart[3][tid]);
     __syncthreads();
-    const uint32_t npair = (uint32_t)(moment_at(sS, 13, 13) + 0.5);
+}
+
+__global__ void __launch_bounds__(kSolveThreads)
+    solve_kernel(const CloudView* __restrict__ clouds, JobDev* __restrict__ jobs,
+                 const double* __restrict__ partials, uint32_t n_partials, IcpDevParams P,
+                 uint32_t* __restrict__ n_active)
+{
+    const uint32_t job = blockIdx.x;
+    JobDev&        J = jobs[job];
+    if (J.status != 0) return;
+    const int tid = threadIdx.x, lane = tid & 31;
+
+    __shared__ double sS[kNumMoments];
+    __shared__ double sPart[kSolveGroups][kNumMoments];
+    __shared__ double sA[144];
+    __shared__ double sG0[12];   // sum a r0
+    __shared__ double sT0[12];   // theta0 layout: [R_i0 R_i1 R_i2 t_i] x 3
+    __shared__ double sR[9], st[3];
+    __shared__ double sX[12], sG12[12], sJ[72], sB[72], sH[36], sg[6];
+    __shared__ int    sStop;
+
+    reduce_moment_partials(partials, job, n_partials, sS, sPart);
+    if (tid < kNumMoments) J.M[tid] = sS[tid];
+    const bool     p2p = (P.matcher_kind == B200ICP_MATCHER_POINTS_DISTANCE);
+    const uint32_t npair = (uint32_t)(pairing_count(sS, p2p) + 0.5);
     if (npair == 0)
     {
         if (tid == 0)
@@ -376,13 +534,13 @@ __global__ void __launch_bounds__(kSolveThreads)
         }
         return;
     }
-    for (int e = tid; e < 144; e += blockDim.x) sA[e] = moment_at(sS, e / 12, e % 12);
+    for (int e = tid; e < 144; e += blockDim.x) sA[e] = normal_matrix_at(sS, p2p, e / 12, e % 12);
     if (tid < 12)
     {
         const int    i = tid >> 2, j = tid & 3;
         const double v = (j < 3) ? J.R[i * 3 + j] : J.t[i];
         sT0[tid] = v;
-        sG0[tid] = moment_at(sS, tid, 12);
+        sG0[tid] = p2p ? moment_at(sS, j, 4 + i) : moment_at(sS, tid, 12);
         if (j < 3)
             sR[i * 3 + j] = v;
         else
@@ -480,37 +638,176 @@ __global__ void __launch_bounds__(kSolveThreads)
     }
     if (lane == 0)
     {
-        // convergence (A.7): delta = log(T0^-1 * Tnew), T0 = previous solution
-        Pose T0, Tn, dT;
-        for (int i = 0; i < 9; i++) T0.R[i] = J.R[i], Tn.R[i] = sR[i];
-        for (int i = 0; i < 3; i++) T0.t[i] = J.t[i], Tn.t[i] = st[i];
-        pose_inverse_compose(T0, Tn, dT);
-        double d[6];
-        se3_log(dT, d);
-        const double dxyz = sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
-        const double drot = sqrt((d[3] * d[3] + d[4] * d[4]) + d[5] * d[5]);
-        for (int i = 0; i < 9; i++) J.Rprev[i] = T0.R[i], J.R[i] = Tn.R[i];
-        for (int i = 0; i < 3; i++) J.tprev[i] = T0.t[i], J.t[i] = Tn.t[i];
-        J.n_pairings = npair;
-        J.inner_iters_total += inner;
-        if (dxyz < P.min_abs_step_trans && drot < P.min_abs_step_rot)
+        Pose Tn;
+        for (int i = 0; i < 9; i++) Tn.R[i] = sR[i];
+        for (int i = 0; i < 3; i++) Tn.t[i] = st[i];
+        finish_outer_iteration(J, Tn, npair, inner, P, n_active);
+    }
+}
+
+// ------------------------------------------------------------ Horn (row N)
+// optimal_tf_horn on the pairings the matcher left in the pair buffer, with the
+// pairings-weight rules of row M.  Two passes over the pairings (A.10):
+//   phase 0: centroids of ALL pairings (sum p, sum q, count)
+//   phase 1: per pairing b = p - pc, a = q - qc; scale-outlier rule; optional
+//            robust weight; S += w b a^T; pairs used
+// then N(S) (4x4), its top eigenvector = quaternion, t = qc - R pc.
+constexpr int kHornVals = 16;   // doubles per CTA partial of either phase
+constexpr int kHornThreads = 256;
+
+// centroids from the phase-0 partials, in one fixed order (used by every CTA
+// of phase 1 and by the final solve: all must see the same bits)
+__device__ __forceinline__ void horn_centroids(const double* __restrict__ part0, uint32_t n_part,
+                                               double* pc, double* qc, double& count)
+{
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (uint32_t c = 0; c < n_part; c++)
+#pragma unroll
+        for (int i = 0; i < 7; i++) acc[i] += part0[(size_t)c * kHornVals + i];
+    count = acc[6];
+    const double n = acc[6] > 0 ? acc[6] : 1.0;
+    for (int d = 0; d < 3; d++) pc[d] = acc[d] / n, qc[d] = acc[3 + d] / n;
+}
+
+__global__ void __launch_bounds__(kHornThreads)
+    horn_sum_kernel(const CloudView* __restrict__ clouds, const JobDev* __restrict__ jobs,
+                    const PairRec* __restrict__ pairs, const double* __restrict__ part0,
+                    double* __restrict__ part_out, IcpDevParams P, int phase)
+{
+    const uint32_t job = blockIdx.y;
+    const JobDev&  J = jobs[job];
+    if (J.status != 0) return;
+    const CloudView cvL = clouds[J.to_cloud];
+    const PairRec*  prec = pairs + J.pair_base;
+    const uint32_t  n = cvL.grid->n_valid;
+    __shared__ double sc[8];
+    __shared__ double sred[kHornThreads / 32][kHornVals];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (phase == 1)
+    {
+        if (tid == 0)
         {
-            J.status = 1;
-            J.term_reason = B200ICP_TERM_STALLED;
-            atomicSub(n_active, 1u);
+            double pc[3], qc[3], cnt;
+            horn_centroids(part0 + (size_t)job * gridDim.x * kHornVals, gridDim.x, pc, qc, cnt);
+            for (int d = 0; d < 3; d++) sc[d] = pc[d], sc[3 + d] = qc[d];
         }
-        else
+        __syncthreads();
+    }
+    double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint32_t pos = blockIdx.x * kHornThreads + tid; pos < n; pos += gridDim.x * kHornThreads)
+    {
+        const PairRec r = prec[pos];
+        if (!r.paired) continue;
+        const float4 pl = __ldg(cvL.pts + pos);
+        const double p[3] = {(double)pl.x, (double)pl.y, (double)pl.z};
+        if (phase == 0)
         {
-            const uint32_t it = J.iter + 1;
-            J.iter = it;
-            if (it >= P.max_iterations)
+            acc[0] += p[0], acc[1] += p[1], acc[2] += p[2];
+            acc[3] += r.q[0], acc[4] += r.q[1], acc[5] += r.q[2];
+            acc[6] += 1.0;
+            continue;
+        }
+        const double b[3] = {p[0] - sc[0], p[1] - sc[1], p[2] - sc[2]};           // local, centroid-relative
+        const double a[3] = {r.q[0] - sc[3], r.q[1] - sc[4], r.q[2] - sc[5]};     // global
+        const double bn = sqrt((b[0] * b[0] + b[1] * b[1]) + b[2] * b[2]);
+        const double an = sqrt((a[0] * a[0] + a[1] * a[1]) + a[2] * a[2]);
+        double       w = 1.0;
+        if (P.use_scale_outlier_detector)
+        {  // row M
+            const double mx = bn > an ? bn : an, mn = bn > an ? an : bn;
+            if (!(mn > 0.0) || mx / mn > P.scale_outlier_threshold) continue;
+        }
+        if (P.use_robust_kernel && bn > 0 && an > 0)
+        {
+            const double bu[3] = {b[0] / bn, b[1] / bn, b[2] / bn};
+            double       rb[3];
+            mat3_vec(J.R, bu, rb);
+            double cs = (rb[0] * a[0] + rb[1] * a[1] + rb[2] * a[2]) / an;
+            cs = cs > 1 ? 1 : (cs < -1 ? -1 : cs);
+            const double ang = acos(cs);
+            if (ang > P.robust_kernel_param)
             {
-                J.status = 1;
-                J.term_reason = B200ICP_TERM_MAX_ITERATIONS;
-                atomicSub(n_active, 1u);
+                const double e = ang - P.robust_kernel_param;
+                w *= 1.0 / (1.0 + P.robust_kernel_scale * e * e);
             }
         }
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) acc[i * 3 + k] += w * b[i] * a[k];
+        acc[9] += 1.0;
     }
+#pragma unroll
+    for (int i = 0; i < 10; i++)
+    {
+        double v = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if (lane == 0) sred[warp][i] = v;
+    }
+    __syncthreads();
+    if (tid < kHornVals)
+    {
+        double v = 0;
+        if (tid < 10)
+            for (int w = 0; w < kHornThreads / 32; w++) v += sred[w][tid];
+        part_out[((size_t)job * gridDim.x + blockIdx.x) * kHornVals + tid] = v;
+    }
+}
+
+__global__ void __launch_bounds__(kSolveThreads)
+    horn_solve_kernel(JobDev* __restrict__ jobs, const double* __restrict__ partials,
+                      uint32_t n_partials, const double* __restrict__ part0,
+                      const double* __restrict__ part1, uint32_t n_hpart, IcpDevParams P,
+                      uint32_t* __restrict__ n_active)
+{
+    const uint32_t job = blockIdx.x;
+    JobDev&        J = jobs[job];
+    if (J.status != 0) return;
+    const int tid = threadIdx.x;
+    __shared__ double sS[kNumMoments];
+    __shared__ double sPart[kSolveGroups][kNumMoments];
+    __shared__ double sH[kHornVals];
+    // the matcher's moments are only needed for the covariance at the end
+    reduce_moment_partials(partials, job, n_partials, sS, sPart);
+    if (tid < kNumMoments) J.M[tid] = sS[tid];
+    if (tid < 10)
+    {
+        double        v = 0;
+        const double* p = part1 + (size_t)job * n_hpart * kHornVals + tid;
+        for (uint32_t c = 0; c < n_hpart; c++) v += p[(size_t)c * kHornVals];
+        sH[tid] = v;
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    double pc[3], qc[3], cnt;
+    horn_centroids(part0 + (size_t)job * n_hpart * kHornVals, n_hpart, pc, qc, cnt);
+    const uint32_t npair = (uint32_t)(cnt + 0.5);
+    if (npair == 0)
+    {
+        J.n_pairings = 0;
+        J.status = 1;
+        J.term_reason = B200ICP_TERM_NO_PAIRINGS;
+        atomicSub(n_active, 1u);
+        return;
+    }
+    const uint32_t used = (uint32_t)(sH[9] + 0.5);
+    if (used < 3)
+    {  // Solver error: the pose is left as it was
+        J.n_pairings = npair;
+        J.status = 1;
+        J.term_reason = B200ICP_TERM_SOLVER_ERROR;
+        atomicSub(n_active, 1u);
+        return;
+    }
+    double q[4];
+    horn_quaternion(sH, q);
+    Pose Tn;
+    quaternion_to_R(q, Tn.R);
+    double Rp[3];
+    mat3_vec(Tn.R, pc, Rp);
+    for (int d = 0; d < 3; d++) Tn.t[d] = qc[d] - Rp[d];
+    finish_outer_iteration(J, Tn, npair, 1u, P, n_active);
 }
 
 // ------------------------------------------------------------------ quality
@@ -532,7 +829,7 @@ __global__ void __launch_bounds__(kChunk)
     const uint64_t sent = sentinel_key(P.q_thr2);
     uint32_t       hits = 0;
     for_each_item<1>(sm.tile[tid >> 5], cvL, cvG, sm.grid, sm.Rt, n_items, P.q_thr2,
-        [&](bool has, const float4&, double, double, double, float, float, float, uint64_t (&key)[1]) {
+        [&](bool has, uint32_t, const float4&, double, double, double, float, float, float, uint64_t (&key)[1]) {
             if (has && (key[0] != sent) && (key_d2(key[0]) < P.q_thr2)) hits++;  // strict
         });
     // integer count: any order gives the same sum
@@ -549,13 +846,14 @@ __global__ void __launch_bounds__(64) covariance_kernel(JobDev* __restrict__ job
     JobDev&   J = jobs[blockIdx.x];
     const int tid = threadIdx.x;
     __shared__ double sA[144], sD[72], sH[36];
+    const bool p2p = (P.matcher_kind == B200ICP_MATCHER_POINTS_DISTANCE);
     if (J.n_pairings == 0)
     {
         if (tid < 36) J.cov[tid] = 0.0;
         if (tid == 0) J.cov_singular = 1;
         return;
     }
-    for (int e = tid; e < 144; e += blockDim.x) sA[e] = moment_at(J.M, e / 12, e % 12);
+    for (int e = tid; e < 144; e += blockDim.x) sA[e] = normal_matrix_at(J.M, p2p, e / 12, e % 12);
     if (tid < 6)
     {
         Pose T;
@@ -615,7 +913,7 @@ __global__ void __launch_bounds__(kChunk)
     const uint32_t n_items = (sm.grid.n_valid > 0) ? sm.n_items : 0u;
     const uint64_t sent = sentinel_key(cap_d2);
     for_each_item<K>(sm.tile[tid >> 5], cvL, cvG, sm.grid, sm.Rt, n_items, cap_d2,
-        [&](bool has, const float4& pl, double, double, double, float, float, float, uint64_t (&key)[K]) {
+        [&](bool has, uint32_t, const float4& pl, double, double, double, float, float, float, uint64_t (&key)[K]) {
             if (!has) return;
             const uint32_t orig = __float_as_uint(pl.w);
 #pragma unroll
@@ -672,35 +970,36 @@ static uint32_t ctas_per_job(const ::b200icp* ctx, size_t max_points, size_t njo
 }
 
 template <bool WRITE>
-static void launch_match(Workspace* ws, uint32_t knn, dim3 grid, const CloudView* d_clouds,
-                         const JobDev* d_jobs, double* d_partials, const IcpDevParams& D,
-                         const MatchOut& mo)
+static void launch_match(Workspace* ws, const IcpDevParams& D, dim3 grid, const CloudView* d_clouds,
+                         const JobDev* d_jobs, double* d_partials, const MatchOut& mo, PairRec* d_pairs)
 {
-    if (knn == 6)
-        match_kernel<6, WRITE><<<grid, kChunk, 0, ws->stream>>>(d_clouds, d_jobs, d_partials, D, mo);
-    else if (knn <= 4)
-        match_kernel<4, WRITE><<<grid, kChunk, 0, ws->stream>>>(d_clouds, d_jobs, d_partials, D, mo);
+    cudaStream_t s = ws->stream;
+    if (D.matcher_kind == B200ICP_MATCHER_POINTS_DISTANCE)
+        match_p2p_kernel<WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_partials, D, mo, d_pairs);
+    else if (D.knn == 6)
+        match_kernel<6, WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_partials, D, mo, d_pairs);
+    else if (D.knn <= 4)
+        match_kernel<4, WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_partials, D, mo, d_pairs);
     else
-        match_kernel<8, WRITE><<<grid, kChunk, 0, ws->stream>>>(d_clouds, d_jobs, d_partials, D, mo);
+        match_kernel<8, WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_partials, D, mo, d_pairs);
     ws->launches++;
 }
 
 static int check_supported(const ::b200icp* ctx)
 {
     const auto& P = ctx->P;
-    if (P.matcher_kind != B200ICP_MATCHER_POINT2PLANE || P.solver_kind != B200ICP_SOLVER_GAUSS_NEWTON)
+    if ((P.matcher_kind != B200ICP_MATCHER_POINT2PLANE && P.matcher_kind != B200ICP_MATCHER_POINTS_DISTANCE) ||
+        (P.solver_kind != B200ICP_SOLVER_GAUSS_NEWTON && P.solver_kind != B200ICP_SOLVER_HORN))
     {
-        set_error("this build runs Matcher_Point2Plane + Solver_GaussNewton on the device; "
-                  "matcher_kind=%d solver_kind=%d is not available yet",
-                  P.matcher_kind, P.solver_kind);
+        set_error("unknown matcher_kind=%d / solver_kind=%d", P.matcher_kind, P.solver_kind);
         return B200ICP_ERR_UNSUPPORTED;
     }
-    if (P.knn < 1 || P.knn > B200ICP_MAX_KNN)
+    if (P.matcher_kind == B200ICP_MATCHER_POINT2PLANE && (P.knn < 1 || P.knn > B200ICP_MAX_KNN))
     {
         set_error("knn=%u outside [1,%d]", P.knn, B200ICP_MAX_KNN);
         return B200ICP_ERR_UNSUPPORTED;
     }
-    if (P.use_robust_kernel)
+    if (P.use_robust_kernel && P.solver_kind == B200ICP_SOLVER_GAUSS_NEWTON)
     {
         set_error("use_robust_kernel=true is not available with Solver_GaussNewton");
         return B200ICP_ERR_UNSUPPORTED;
@@ -738,19 +1037,35 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
         memcpy(J.Rprev, T.R, sizeof(T.R)), memcpy(J.tprev, T.t, sizeof(T.t));
         J.from_cloud = add(from[j]);
         J.to_cloud = add(to[j]);
+        J.pair_base = (uint32_t)total_queries;
         max_points = std::max(max_points, to[j]->n);
         total_queries += to[j]->n;
+    }
+    const bool horn = (D.solver_kind == B200ICP_SOLVER_HORN);
+    if (horn && total_queries >= 0xFFFFFFFFull)
+    {
+        set_error("too many points in one batch for the Horn pair buffer");
+        return B200ICP_ERR_BAD_ARG;
     }
     for (auto& kv : cmap)
         if (int r = wait_cloud(ws, kv.first)) return r;
     const uint32_t G = ctas_per_job(ctx, max_points, n);
 
+    const uint32_t GH = std::max<uint32_t>(1, std::min<uint32_t>(G, (uint32_t)((max_points + 1023) / 1024)));
+    PairRec*       d_pairs = nullptr;
+    double *       d_h0 = nullptr, *d_h1 = nullptr;
     Carver sz(nullptr);
     auto layout = [&](Carver& k, CloudView*& dc, JobDev*& dj, double*& dp, uint32_t*& da) {
         dc = k.take<CloudView>(views.size());
         dj = k.take<JobDev>(n);
         dp = k.take<double>((size_t)n * G * kNumMoments);
         da = k.take<uint32_t>(4);
+        if (horn)
+        {
+            d_pairs = k.take<PairRec>(total_queries ? total_queries : 1);
+            d_h0 = k.take<double>((size_t)n * GH * kHornVals);
+            d_h1 = k.take<double>((size_t)n * GH * kHornVals);
+        }
     };
     CloudView* d_clouds;
     JobDev*    d_jobs;
@@ -792,11 +1107,23 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
         for (uint32_t i = 0; i < todo; i++, enq++)
         {
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 0], s));
-            launch_match<false>(ws, D.knn, mgrid, d_clouds, d_jobs, d_partials, D, no_out);
+            launch_match<false>(ws, D, mgrid, d_clouds, d_jobs, d_partials, no_out, d_pairs);
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 1], s));
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 2], s));
-            solve_kernel<<<(unsigned)n, kSolveThreads, 0, s>>>(d_clouds, d_jobs, d_partials, G, D, d_active);
-            ws->launches++;
+            if (horn)
+            {
+                const dim3 hgrid(GH, (unsigned)n);
+                horn_sum_kernel<<<hgrid, kHornThreads, 0, s>>>(d_clouds, d_jobs, d_pairs, nullptr, d_h0, D, 0);
+                horn_sum_kernel<<<hgrid, kHornThreads, 0, s>>>(d_clouds, d_jobs, d_pairs, d_h0, d_h1, D, 1);
+                horn_solve_kernel<<<(unsigned)n, kSolveThreads, 0, s>>>(d_jobs, d_partials, G, d_h0, d_h1, GH, D,
+                                                                        d_active);
+                ws->launches += 3;
+            }
+            else
+            {
+                solve_kernel<<<(unsigned)n, kSolveThreads, 0, s>>>(d_clouds, d_jobs, d_partials, G, D, d_active);
+                ws->launches++;
+            }
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 3], s));
         }
         // the host stays one batch ahead of the device: it only looks at the
@@ -1004,7 +1331,7 @@ int run_match(::b200icp* ctx, const b200icp_cloud* from, const b200icp_cloud* to
     Workspace*          ws = L.ws;
     cudaStream_t        s = ws->stream;
     const IcpDevParams& D = ctx->D;
-    const size_t        n = to->n, k = D.knn;
+    const size_t        n = to->n, k = (D.matcher_kind == B200ICP_MATCHER_POINTS_DISTANCE) ? 1 : D.knn;
     if (n_pairings) *n_pairings = 0;
     if (n == 0) return B200ICP_OK;
     const uint32_t G = ctas_per_job(ctx, n, 1);
@@ -1026,7 +1353,7 @@ int run_match(::b200icp* ctx, const b200icp_cloud* from, const b200icp_cloud* to
     B2_CUDA_TRY(cudaMemsetAsync(mo.nn_idx, 0xFF, n * k * sizeof(uint32_t), s));
     B2_CUDA_TRY(cudaMemsetAsync(mo.centroid, 0, n * 3 * sizeof(double), s));
     B2_CUDA_TRY(cudaMemsetAsync(mo.normal, 0, n * 3 * sizeof(double), s));
-    launch_match<true>(ws, D.knn, dim3(G, 1), sj.d_clouds, sj.d_jobs, d_partials, D, mo);
+    launch_match<true>(ws, D, dim3(G, 1), sj.d_clouds, sj.d_jobs, d_partials, mo, nullptr);
     B2_CUDA_TRY(cudaGetLastError());
     std::vector<double> part((size_t)G * kNumMoments);
     B2_CUDA_TRY(cudaMemcpyAsync(part.data(), d_partials, part.size() * sizeof(double),
@@ -1044,7 +1371,8 @@ int run_match(::b200icp* ctx, const b200icp_cloud* from, const b200icp_cloud* to
     if (n_pairings)
     {
         double cnt = 0;
-        for (uint32_t c = 0; c < G; c++) cnt += moment_at(part.data() + (size_t)c * kNumMoments, 13, 13);
+        const bool p2p = (D.matcher_kind == B200ICP_MATCHER_POINTS_DISTANCE);
+        for (uint32_t c = 0; c < G; c++) cnt += pairing_count(part.data() + (size_t)c * kNumMoments, p2p);
         *n_pairings = (uint32_t)(cnt + 0.5);
     }
     return B200ICP_OK;

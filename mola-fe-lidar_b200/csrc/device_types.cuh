@@ -76,7 +76,7 @@ struct JobDev
     uint32_t cov_singular;
     uint32_t from_cloud, to_cloud;  // indices into the launch's CloudView table
     uint32_t inner_iters_total;
-    uint32_t pad;
+    uint32_t pair_base;    // first PairRec of this job in the launch's pair buffer (Horn)
 };
 
 struct IcpDevParams
@@ -96,6 +96,22 @@ struct IcpDevParams
     float    q_thr2;    // quality: (float)thresholdDistance squared in float (A.8)
     float    q_thr;
     double   cov_fd_step;
+    int32_t  solver_kind;
+    // pairingsWeightParameters (row M): consumed by the Horn solver
+    int32_t  use_scale_outlier_detector;
+    double   scale_outlier_threshold;
+    int32_t  use_robust_kernel;
+    double   robust_kernel_param, robust_kernel_scale;
+};
+
+// One pairing as the closed-form (Horn) solver consumes it: the global-side
+// point (nearest neighbour, or the plane centroid for Matcher_Point2Plane);
+// the local point is pts[position]. 32 bytes, indexed by sorted position.
+struct PairRec
+{
+    double   q[3];
+    uint32_t paired;
+    uint32_t pad;
 };
 
 __host__ __device__ inline uint32_t hash_slot(uint32_t key, uint32_t shift)

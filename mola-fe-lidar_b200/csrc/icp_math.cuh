@@ -261,6 +261,75 @@ B2_HD void jacobi3(double* A, double* ev, double* V)
     }
 }
 
+// Cyclic Jacobi for a symmetric 4x4 (Horn's N matrix, row N / A.10):
+// eigenvector of the LARGEST eigenvalue -> unit quaternion (w, x, y, z), w >= 0.
+B2_HD void horn_quaternion(const double* S /* 3x3 cross-covariance, row-major */, double* q)
+{
+    const double Sxx = S[0], Sxy = S[1], Sxz = S[2], Syx = S[3], Syy = S[4], Syz = S[5],
+                 Szx = S[6], Szy = S[7], Szz = S[8];
+    double A[16] = {Sxx + Syy + Szz, Syz - Szy,       Szx - Sxz,        Sxy - Syx,
+                    Syz - Szy,       Sxx - Syy - Szz, Sxy + Syx,        Szx + Sxz,
+                    Szx - Sxz,       Sxy + Syx,       -Sxx + Syy - Szz, Syz + Szy,
+                    Sxy - Syx,       Szx + Sxz,       Syz + Szy,        -Sxx - Syy + Szz};
+    double V[16];
+    for (int i = 0; i < 16; i++) V[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    double frob = 0;
+    for (int i = 0; i < 16; i++) frob += A[i] * A[i];
+    const double tol = 1e-30 * frob;
+    for (int sweep = 0; sweep < 30; sweep++)
+    {
+        double off = 0;
+        for (int p = 0; p < 4; p++)
+            for (int r = p + 1; r < 4; r++) off += A[p * 4 + r] * A[p * 4 + r];
+        if (!(off > tol)) break;
+        for (int p = 0; p < 4; p++)
+            for (int r = p + 1; r < 4; r++)
+            {
+                const double apq = A[p * 4 + r];
+                if (apq == 0.0) continue;
+                const double theta = (A[r * 4 + r] - A[p * 4 + p]) / (2.0 * apq);
+                const double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(tt * tt + 1.0);
+                const double s = tt * c;
+                A[p * 4 + p] = A[p * 4 + p] - tt * apq;
+                A[r * 4 + r] = A[r * 4 + r] + tt * apq;
+                A[p * 4 + r] = A[r * 4 + p] = 0.0;
+                for (int k = 0; k < 4; k++)
+                {
+                    if (k != p && k != r)
+                    {
+                        const double akp = A[k * 4 + p], akr = A[k * 4 + r];
+                        const double np_ = c * akp - s * akr;
+                        const double nr_ = s * akp + c * akr;
+                        A[k * 4 + p] = A[p * 4 + k] = np_;
+                        A[k * 4 + r] = A[r * 4 + k] = nr_;
+                    }
+                    const double vkp = V[k * 4 + p], vkr = V[k * 4 + r];
+                    V[k * 4 + p] = c * vkp - s * vkr;
+                    V[k * 4 + r] = s * vkp + c * vkr;
+                }
+            }
+    }
+    // the oracle sorts ascending (stable, strict '>') and takes the last
+    // column: that is the LAST index among equal maxima
+    int best = 0;
+    for (int i = 1; i < 4; i++)
+        if (!(A[best * 5] > A[i * 5])) best = i;
+    double qw = V[0 * 4 + best], qx = V[1 * 4 + best], qy = V[2 * 4 + best], qz = V[3 * 4 + best];
+    const double qn = sqrt(((qw * qw + qx * qx) + qy * qy) + qz * qz);
+    qw /= qn, qx /= qn, qy /= qn, qz /= qn;
+    if (qw < 0) qw = -qw, qx = -qx, qy = -qy, qz = -qz;
+    q[0] = qw, q[1] = qx, q[2] = qy, q[3] = qz;
+}
+
+B2_HD void quaternion_to_R(const double* q, double* R)
+{
+    const double qw = q[0], qx = q[1], qy = q[2], qz = q[3];
+    R[0] = 1 - 2 * (qy * qy + qz * qz), R[1] = 2 * (qx * qy - qw * qz), R[2] = 2 * (qx * qz + qw * qy);
+    R[3] = 2 * (qx * qy + qw * qz), R[4] = 1 - 2 * (qx * qx + qz * qz), R[5] = 2 * (qy * qz - qw * qx);
+    R[6] = 2 * (qx * qz - qw * qy), R[7] = 2 * (qy * qz + qw * qx), R[8] = 1 - 2 * (qx * qx + qy * qy);
+}
+
 // Column-pivoting Householder QR solve, 6x6; rank-revealing like Eigen's
 // default threshold. Returns the rank; rank-deficient systems get the basic
 // solution (zeros in the dependent unknowns).

@@ -99,6 +99,12 @@ void make_dev_params(const b200icp_params_t& P, IcpDevParams& D)
     D.q_thr = (float)P.quality_threshold_distance;
     D.q_thr2 = D.q_thr * D.q_thr;
     D.cov_fd_step = P.cov_fd_step;
+    D.solver_kind = P.solver_kind;
+    D.use_scale_outlier_detector = P.use_scale_outlier_detector;
+    D.scale_outlier_threshold = P.scale_outlier_threshold;
+    D.use_robust_kernel = P.use_robust_kernel;
+    D.robust_kernel_param = P.robust_kernel_param;
+    D.robust_kernel_scale = P.robust_kernel_scale;
 }
 }  // namespace b2
 

@@ -96,7 +96,7 @@ typedef struct b200icp_result
 /* per-kernel device timings, CUDA events on the launching stream */
 typedef struct b200icp_profile
 {
-    uint64_t match_launches;  /* fused transform+kNN+plane-fit+moments kernel */
+    uint64_t match_launches;  /* the matcher's search kernel: transform + exact kNN (tile sweep) */
     double   match_ms;
     uint64_t match_queries;   /* queries processed by those launches */
     uint64_t solve_launches;
@@ -111,6 +111,8 @@ typedef struct b200icp_profile
     double   voxel_ms;
     uint64_t voxel_points;
     uint64_t total_kernel_launches; /* every kernel this library launched */
+    uint64_t fit_launches;    /* plane fit + gates + moments kernel */
+    double   fit_ms;
 } b200icp_profile_t;
 
 typedef struct b200icp       b200icp_t;       /* the mp2p_icp::ICP object + its Parameters */
@@ -164,6 +166,25 @@ int b200icp_voxel_decimate(b200icp_t* icp, const b200icp_cloud_t* in, float reso
 int b200icp_knn(b200icp_t* icp, const b200icp_cloud_t* ref, const b200icp_cloud_t* queries,
                 const double* pose6, uint32_t k, float max_dist, uint32_t* idx_out,
                 float* d2_out);
+
+/* --- sharded maps: per-GPU partial arg-min, merged over NVLink ------------ */
+/* A packed key is (d2 as float32 bits) << 32 | index: its unsigned integer
+ * order IS the (d2, index) order of the tie rule, so partial results of
+ * disjoint map shards merge with a plain minimum (k = 1: an all-reduce MIN on
+ * 64-bit integers; k > 1: b200icp_merge_keys_device after an exchange). */
+#define B200ICP_NO_KEY 0x7F800000FFFFFFFFull /* +inf distance, invalid index */
+/* Same search as b200icp_knn, results left ON THE DEVICE as packed keys
+ * d_keys_out[nq*k] (queries' original order, padded with B200ICP_NO_KEY).
+ * d_index_map (device, optional, [size of ref]): shard-local index -> global
+ * index of the caller's unsharded map; must be increasing so that ties order
+ * alike in both numberings.  Returns after the kernels have completed. */
+int b200icp_knn_keys_device(b200icp_t* icp, const b200icp_cloud_t* ref, const b200icp_cloud_t* queries,
+                            const double* pose6, uint32_t k, float max_dist,
+                            const uint32_t* d_index_map, uint64_t* d_keys_out);
+/* Merges `parts` ascending key lists per query: d_parts[p*part_stride + q*k + i]
+ * -> d_out[q*k + i], the k smallest of the union, ascending (device pointers). */
+int b200icp_merge_keys_device(b200icp_t* icp, const uint64_t* d_parts, uint32_t parts,
+                              size_t part_stride, size_t nq, uint32_t k, uint64_t* d_out);
 
 /* --- matcher at a fixed pose (Matcher_Point2Plane; parity hook) ---------- */
 /* Host outputs in the local cloud's ORIGINAL order: paired[n] (0/1),

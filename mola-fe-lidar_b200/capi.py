@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "lib", "libb200icp.so")
+# B200ICP_LIB: developer override (A/B of two builds on one box)
+LIB_PATH = os.environ.get("B200ICP_LIB") or os.path.join(PKG_DIR, "lib", "libb200icp.so")
 
 INVALID = 0xFFFFFFFF
 TERM = {0: "Undefined", 1: "NoPairings", 2: "SolverError", 3: "MaxIterations", 4: "Stalled"}
@@ -78,6 +79,7 @@ class Profile(C.Structure):
         ("knn_launches", C.c_uint64), ("knn_ms", C.c_double), ("knn_queries", C.c_uint64),
         ("voxel_launches", C.c_uint64), ("voxel_ms", C.c_double), ("voxel_points", C.c_uint64),
         ("total_kernel_launches", C.c_uint64),
+        ("fit_launches", C.c_uint64), ("fit_ms", C.c_double),
     ]
 
     def as_dict(self):
@@ -89,7 +91,8 @@ EXPORTS = [
     "b200icp_params_from_yaml", "b200icp_create", "b200icp_create_from_yaml", "b200icp_destroy",
     "b200icp_get_params", "b200icp_device", "b200icp_cloud_upload", "b200icp_cloud_from_device",
     "b200icp_cloud_free", "b200icp_cloud_size", "b200icp_cloud_download",
-    "b200icp_voxel_decimate", "b200icp_knn", "b200icp_match", "b200icp_align",
+    "b200icp_voxel_decimate", "b200icp_knn", "b200icp_knn_keys_device", "b200icp_merge_keys_device",
+    "b200icp_match", "b200icp_align",
     "b200icp_align_batch", "b200icp_profile_enable", "b200icp_profile_reset",
     "b200icp_profile_get", "b200icp_synchronize",
 ]
@@ -127,6 +130,8 @@ def lib():
     L.b200icp_cloud_download.argtypes = [vp, fp, fp, fp]
     L.b200icp_voxel_decimate.argtypes = [vp, vp, C.c_float, C.c_int, C.c_float, C.POINTER(vp), up]
     L.b200icp_knn.argtypes = [vp, vp, vp, dp, C.c_uint32, C.c_float, up, fp]
+    L.b200icp_knn_keys_device.argtypes = [vp, vp, vp, dp, C.c_uint32, C.c_float, vp, vp]
+    L.b200icp_merge_keys_device.argtypes = [vp, vp, C.c_uint32, C.c_size_t, C.c_size_t, C.c_uint32, vp]
     L.b200icp_match.argtypes = [vp, vp, vp, dp, C.POINTER(C.c_uint8), up, up, dp, dp, up]
     L.b200icp_align.argtypes = [vp, vp, vp, dp, C.POINTER(Result)]
     L.b200icp_align_batch.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(vp), dp,
@@ -268,6 +273,19 @@ class ICP:
                                  None if pose is None else _ptr(pose, C.c_double), k, max_dist,
                                  _ptr(idx, C.c_uint32), _ptr(d2, C.c_float)))
         return idx, d2
+
+    def knn_keys_device(self, ref, queries, k, max_dist, d_keys_out, d_index_map=0, pose6=None):
+        """Same search, packed keys (d2 bits << 32 | index) left on the device at
+        the raw pointer d_keys_out [len(queries) * k] uint64; d_index_map: device
+        pointer of the shard-local -> global index table (0: none)."""
+        pose = None if pose6 is None else np.ascontiguousarray(pose6, dtype=np.float64)
+        _check(lib().b200icp_knn_keys_device(self.h, ref.h, queries.h,
+                                             None if pose is None else _ptr(pose, C.c_double), k, max_dist,
+                                             d_index_map or None, d_keys_out))
+
+    def merge_keys_device(self, d_parts, parts, part_stride, nq, k, d_out):
+        """k smallest of `parts` ascending key lists per query, device pointers."""
+        _check(lib().b200icp_merge_keys_device(self.h, d_parts, parts, part_stride, nq, k, d_out))
 
     def match(self, from_global, to_local, pose6=None):
         # Matcher_Points_DistanceThreshold pairs with the single nearest neighbour

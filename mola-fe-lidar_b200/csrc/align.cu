@@ -2,11 +2,16 @@
 // drives it (LidarOdometry.cpp:869-871),
 // resident on the device for the whole iteration loop.
 //
-// Per outer iteration, two launches over a table of independent jobs:
-//   match_kernel  : per local point -- transform (A.2), radius-capped kNN on
-//                   the grid index (A.3/A.4), plane fit + gates (A.5), and the
-//                   point-to-plane MOMENTS of the pairing, reduced per CTA in a
-//                   fixed-shape tree to partials[job][chunk][74] (f64).
+// Per outer iteration, three launches over a table of independent jobs:
+//   search kernel : per local point -- transform (A.2), radius-capped exact
+//                   kNN on the grid index (A.3/A.4): the tile sweep of
+//                   sweep_search.cuh, one CTA per 32-query item, scheduled
+//                   dynamically (results do not depend on the order) -> the
+//                   neighbour rows nn[job][point][K].
+//   fit kernel    : per local point -- plane fit + gates (A.5) and the
+//                   point-to-plane MOMENTS of the pairing, accumulated per warp
+//                   over a STATIC list of items and reduced per CTA in a
+//                   fixed-shape tree to partials[job][cta][192] (f64).
 //   solve_kernel  : fixed-order reduction of the partials, then the whole
 //                   Gauss-Newton inner loop (A.6) on the 12x12 moment matrix,
 //                   the SE(3) update, the convergence test (A.7) and the job's
@@ -22,9 +27,12 @@
 // per-pairing Gauss-Newton in exact arithmetic.
 #include "icp_math.cuh"
 #include "tile_search.cuh"
+#include "sweep_search.cuh"
 #include "runtime.cuh"
 
 #include <algorithm>
+#include <cfloat>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -84,32 +92,188 @@ struct MatchOut
     double*   normal;
 };
 
-// ---- the item loop shared by the matcher, the quality pass and the kNN query --
-// Each warp takes the items w, w + W, ... of the local cloud (static
-// assignment: fixed summation order).  Per item (<= 32 queries, one per lane):
-// box of the queries' home cells -> tile -> search.  `f` is called by ALL
-// lanes once per item: f(has, pos, pl, gx, gy, gz, qx, qy, qz, key) with `has`
-// false on lanes without a point (their key[] holds sentinels).
-template <int K, class F>
-__device__ __forceinline__ void for_each_item(WarpTile& W, const CloudView& cvL, const CloudView& cvG,
-                                              const GridDev& grid, const double* Rt, uint32_t n_items,
-                                              float cap_d2, F&& f)
+// A.2: q = fl32(R p + t), f64 accumulate in this fixed order (both stages use it)
+__device__ __forceinline__ void transform_point(const double* Rt, const float4& pl, double& gx, double& gy,
+                                                double& gz)
 {
-    const int      lane = threadIdx.x & 31;
-    const int      S = search_shells(grid, cap_d2);
+    const double px = pl.x, py = pl.y, pz = pl.z;
+    gx = ((Rt[0] * px + Rt[1] * py) + Rt[2] * pz) + Rt[9];
+    gy = ((Rt[3] * px + Rt[4] * py) + Rt[5] * pz) + Rt[10];
+    gz = ((Rt[6] * px + Rt[7] * py) + Rt[8] * pz) + Rt[11];
+}
+
+__device__ __forceinline__ bool matcher_active(const IcpDevParams& P, uint32_t it)
+{
+    return (P.run_from_iteration <= it) && (P.run_up_to_iteration == 0 || it <= P.run_up_to_iteration);
+}
+
+// ============================================================== search stage
+// What a search kernel does with the k best keys of one item.  Called by all 32
+// lanes of one warp: lane = query, `has` false on lanes without a point.
+
+// neighbour indices (and squared distances) to a buffer
+struct NnWriter
+{
+    uint32_t* idx;      // [rows * k]
+    float*    d2;       // [rows * k] or null
+    uint32_t  k;        // entries per row (<= K)
+    uint32_t  by_orig;  // row = original index of the query (kNN call) | job base + sorted position (matchers)
+    template <int K>
+    __device__ __forceinline__ void operator()(JobDev& J, bool has, uint32_t pos, uint32_t orig,
+                                               const uint64_t (&key)[K], uint64_t sent) const
+    {
+        if (!has) return;
+        const size_t row = by_orig ? (size_t)orig : (size_t)J.pair_base + pos;
+#pragma unroll
+        for (int i = 0; i < K; i++)
+            if ((uint32_t)i < k)
+            {
+                const bool ok = key[i] != sent;
+                idx[row * k + i] = ok ? key_idx(key[i]) : kInvalid;
+                if (d2) d2[row * k + i] = ok ? key_d2(key[i]) : INFINITY;
+            }
+    }
+};
+
+// packed keys (d2 bits << 32 | index) for the multi-GPU arg-min merge; `map`
+// renumbers shard-local indices to the caller's global ones
+struct KeyWriter
+{
+    uint64_t*       keys;  // [rows * k], row = original index of the query
+    const uint32_t* map;   // or null
+    uint32_t        k;
+    template <int K>
+    __device__ __forceinline__ void operator()(JobDev&, bool has, uint32_t, uint32_t orig,
+                                               const uint64_t (&key)[K], uint64_t sent) const
+    {
+        if (!has) return;
+#pragma unroll
+        for (int i = 0; i < K; i++)
+            if ((uint32_t)i < k)
+            {
+                uint64_t v = B200ICP_NO_KEY;
+                if (key[i] != sent)
+                {
+                    const uint32_t li = key_idx(key[i]);
+                    v = (key[i] & 0xFFFFFFFF00000000ull) | (uint64_t)(map ? __ldg(map + li) : li);
+                }
+                keys[(size_t)orig * k + i] = v;
+            }
+    }
+};
+
+// QualityEvaluator_PairedRatio (row O / A.8): queries with a neighbour at d2 < thr2 (strict)
+struct HitCounter
+{
+    float thr2;
+    template <int K>
+    __device__ __forceinline__ void operator()(JobDev& J, bool has, uint32_t, uint32_t,
+                                               const uint64_t (&key)[K], uint64_t sent) const
+    {
+        const bool     hit = has && (key[0] != sent) && (key_d2(key[0]) < thr2);
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+        // integer count: any order gives the same sum
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&J.quality_count, (uint32_t)__popc(m));
+    }
+};
+
+// Tile sweep (sweep_search.cuh): one CTA of WPI warps per item, items taken
+// grid-stride.  gate != 0: skip finished jobs and iterations at which the
+// matcher does not run.
+template <int K, int WPI, class Epi>
+__global__ void __launch_bounds__(32 * WPI)
+    search_sweep_kernel(const CloudView* __restrict__ clouds, JobDev* __restrict__ jobs, IcpDevParams P,
+                        float cap_d2, int gate, Epi epi)
+{
+    JobDev& J = jobs[blockIdx.y];
+    if (gate && (J.status != 0 || !matcher_active(P, J.iter))) return;
+    const CloudView cvL = clouds[J.to_cloud];
+    const CloudView cvG = clouds[J.from_cloud];
+
+    __shared__ float4  stage[WPI][kSweepCap];
+    __shared__ GridDev sgrid;
+    __shared__ double  sRt[12];
+    __shared__ uint32_t s_items;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 12) sRt[tid] = (tid < 9) ? J.R[tid] : J.t[tid - 9];
+    if (tid == 12) sgrid = *cvG.grid;
+    if (tid == 13) s_items = cvL.grid->n_items;
+    __syncthreads();
+    const uint32_t n_items = (sgrid.n_valid > 0) ? s_items : 0u;
     const uint64_t sent = sentinel_key(cap_d2);
-    for (uint32_t item = item_warp_id(); item < n_items; item += item_warp_count())
+
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x)
     {
         const uint32_t first = __ldg(cvL.item_first + item);
         const uint32_t cnt = __ldg(cvL.item_first + item + 1) - first;
         const bool     has = (uint32_t)lane < cnt;
         float4         pl = make_float4(0.f, 0.f, 0.f, 0.f);
         if (has) pl = __ldg(cvL.pts + first + lane);
-        const double px = pl.x, py = pl.y, pz = pl.z;
-        // A.2: q = fl32(R p + t), f64 accumulate in this fixed order
-        const double gx = ((Rt[0] * px + Rt[1] * py) + Rt[2] * pz) + Rt[9];
-        const double gy = ((Rt[3] * px + Rt[4] * py) + Rt[5] * pz) + Rt[10];
-        const double gz = ((Rt[6] * px + Rt[7] * py) + Rt[8] * pz) + Rt[11];
+        double gx, gy, gz;
+        transform_point(sRt, pl, gx, gy, gz);
+        const float qx = (float)gx, qy = (float)gy, qz = (float)gz;
+        const bool  valid = has && (fabsf(qx) <= FLT_MAX) && (fabsf(qy) <= FLT_MAX) && (fabsf(qz) <= FLT_MAX);
+        uint64_t    key[K];
+#pragma unroll
+        for (int i = 0; i < K; i++) key[i] = sent;
+        sweep_search<K>(stage[warp], cvG, sgrid, valid, qx, qy, qz, cap_d2, warp, WPI, key);
+        if (WPI > 1)
+        {  // merge the warps' sorted lists into warp 0's
+            uint64_t* mine = reinterpret_cast<uint64_t*>(stage[warp]);
+            if (warp != 0)
+            {
+#pragma unroll
+                for (int i = 0; i < K; i++) mine[i * 32 + lane] = key[i];
+            }
+            __syncthreads();
+            if (warp == 0)
+            {
+                for (int w = 1; w < WPI; w++)
+                {
+                    const uint64_t* other = reinterpret_cast<const uint64_t*>(stage[w]);
+#pragma unroll
+                    for (int i = 0; i < K; i++)
+                    {
+                        const uint64_t kk = other[i * 32 + lane];
+                        if (kk < key[K - 1]) topk_insert<K>(key, kk);
+                    }
+                }
+            }
+        }
+        if (warp == 0) epi(J, has, first + lane, __float_as_uint(pl.w), key, sent);
+        if (WPI > 1) __syncthreads();  // the staging buffers are reused by the next item
+    }
+}
+
+// development probe (B200ICP_DBG_ITEMS=1, kNN call only): cycles spent per item, top bit = fallback search
+__device__ uint32_t* g_dbg_item_cycles = nullptr;
+
+// ---- the per-lane shell walk (tile_search.cuh) as the search stage ----------
+// Warps draw items from the job's counter (dynamic: the results do not depend
+// on who searches what, and items differ a lot in cost).  Per item (<= 32
+// queries, one per lane): box of the queries' home cells -> tile -> search.
+template <int K, class F>
+__device__ __forceinline__ void for_each_item(WarpTile& W, const CloudView& cvL, const CloudView& cvG,
+                                              const GridDev& grid, const double* Rt, uint32_t n_items,
+                                              uint32_t* next_item, float cap_d2, F&& f)
+{
+    const int      lane = threadIdx.x & 31;
+    const int      S = search_shells(grid, cap_d2);
+    const uint64_t sent = sentinel_key(cap_d2);
+    for (;;)
+    {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(next_item, 1u);
+        item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        if (item >= n_items) break;
+        const long long dbg_t0 = g_dbg_item_cycles ? clock64() : 0;
+        const uint32_t first = __ldg(cvL.item_first + item);
+        const uint32_t cnt = __ldg(cvL.item_first + item + 1) - first;
+        const bool     has = (uint32_t)lane < cnt;
+        float4         pl = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has) pl = __ldg(cvL.pts + first + lane);
+        double gx, gy, gz;
+        transform_point(Rt, pl, gx, gy, gz);
         const float  qx = (float)gx, qy = (float)gy, qz = (float)gz;
         const QueryCell qc = locate_query(grid, S, qx, qy, qz);
         const bool      hasq = has && qc.valid;
@@ -133,10 +297,44 @@ __device__ __forceinline__ void for_each_item(WarpTile& W, const CloudView& cvL,
             else
                 knn_search<K>(cvG, grid, qx, qy, qz, cap_d2, key);
         }
-        f(has, first + lane, pl, gx, gy, gz, qx, qy, qz, key);
+        f(has, first + lane, __float_as_uint(pl.w), key);
+        if (g_dbg_item_cycles && lane == 0)
+            g_dbg_item_cycles[item] = (uint32_t)min((long long)0x7FFFFFFF, clock64() - dbg_t0) | (tiled ? 0u : 0x80000000u);
     }
 }
 
+struct SearchSmem
+{
+    WarpTile tile[kChunk / 32];
+    GridDev  grid;
+    double   Rt[12];
+    uint32_t n_items;
+};
+
+template <int K, class Epi>
+__global__ void __launch_bounds__(kChunk)
+    search_tile_kernel(const CloudView* __restrict__ clouds, JobDev* __restrict__ jobs, IcpDevParams P,
+                       float cap_d2, int gate, Epi epi)
+{
+    JobDev& J = jobs[blockIdx.y];
+    if (gate && (J.status != 0 || !matcher_active(P, J.iter))) return;
+    const CloudView cvL = clouds[J.to_cloud];
+    const CloudView cvG = clouds[J.from_cloud];
+    __shared__ SearchSmem sm;
+    const int tid = threadIdx.x;
+    if (tid < 12) sm.Rt[tid] = (tid < 9) ? J.R[tid] : J.t[tid - 9];
+    if (tid == 12) sm.grid = *cvG.grid;
+    if (tid == 13) sm.n_items = cvL.grid->n_items;
+    __syncthreads();
+    const uint32_t n_items = (sm.grid.n_valid > 0) ? sm.n_items : 0u;
+    const uint64_t sent = sentinel_key(cap_d2);
+    for_each_item<K>(sm.tile[tid >> 5], cvL, cvG, sm.grid, sm.Rt, n_items, &J.next_item, cap_d2,
+                     [&](bool has, uint32_t pos, uint32_t orig, uint64_t (&key)[K]) {
+                         epi(J, has, pos, orig, key, sent);
+                     });
+}
+
+// ================================================================= fit stage
 // Adds e e^T of the warp's (<= 32) pairings to the DMMA accumulators: the 16
 // doubles of every paired lane go through the warp's staging buffer, half a
 // warp at a time; groups of four lanes without a pairing are skipped.
@@ -191,27 +389,24 @@ __device__ __forceinline__ void write_cta_partial(double* wbuf, const double (&c
         partial[i] = (wbuf[i] + wbuf[kNumMoments + i]) + (wbuf[2 * kNumMoments + i] + wbuf[3 * kNumMoments + i]);
 }
 
-struct SearchSmem
+struct FitSmem
 {
-    WarpTile tile[kChunk / 32];
-    GridDev  grid;
+    double   stage[kChunk / 32][16 * kStageStride];  // half a warp of e-vectors per round; later the CTA partial
     double   Rt[12];
     uint32_t n_items;
 };
+static_assert(16 * kStageStride >= kNumMoments, "the stage buffers double as the CTA partial");
 
-struct MatchSmem
-{
-    SearchSmem S;
-    double     stage[kChunk / 32][16 * kStageStride];  // half a warp of e-vectors per round
-};
-
-// ------------------------------------------------------------------ matcher
-// grid = (CTAs per job, jobs)
+// Matcher_Point2Plane after the search (rows H, J) + the per-pairing part of
+// optimal_tf_gauss_newton (rows K, L).  One thread per local point, in the
+// cloud's sorted order; warp w takes the items w, w + W, ... (static: the
+// summation order of the moments never depends on scheduling).
+// grid = (CTAs per job, jobs).  nn = [job base + sorted position][K].
 template <int K, bool WRITE>
-__global__ void __launch_bounds__(kChunk, 5)
-    match_kernel(const CloudView* __restrict__ clouds, const JobDev* __restrict__ jobs,
-                 double* __restrict__ partials, IcpDevParams P, MatchOut out,
-                 PairRec* __restrict__ pairs)
+__global__ void __launch_bounds__(kChunk)
+    fit_plane_kernel(const CloudView* __restrict__ clouds, const JobDev* __restrict__ jobs,
+                     const uint32_t* __restrict__ nn, double* __restrict__ partials, IcpDevParams P,
+                     MatchOut out, PairRec* __restrict__ pairs)
 {
     const uint32_t job = blockIdx.y;
     const JobDev&  J = jobs[job];
@@ -219,36 +414,49 @@ __global__ void __launch_bounds__(kChunk, 5)
     const CloudView cvL = clouds[J.to_cloud];
     const CloudView cvG = clouds[J.from_cloud];
     PairRec*        prec = pairs ? pairs + J.pair_base : nullptr;
+    const uint32_t* nnj = nn + (size_t)J.pair_base * K;
 
-    __shared__ MatchSmem sm;
+    __shared__ FitSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 12) sm.S.Rt[tid] = (tid < 9) ? J.R[tid] : J.t[tid - 9];
-    if (tid == 32) sm.S.grid = *cvG.grid;
-    if (tid == 64) sm.S.n_items = cvL.grid->n_items;
+    if (tid < 12) sm.Rt[tid] = (tid < 9) ? J.R[tid] : J.t[tid - 9];
+    if (tid == 32) sm.n_items = (cvG.grid->n_valid > 0) ? cvL.grid->n_items : 0u;
     __syncthreads();
-
-    const uint32_t it = J.iter;
-    const bool     active = (P.run_from_iteration <= it) &&
-                        (P.run_up_to_iteration == 0 || it <= P.run_up_to_iteration);
-    const uint32_t n_items = (active && sm.S.grid.n_valid > 0) ? sm.S.n_items : 0u;
-    const uint64_t sent = sentinel_key(P.thr2);
+    const uint32_t n_items = matcher_active(P, J.iter) ? sm.n_items : 0u;
     double         c00[2] = {0, 0}, c01[2] = {0, 0}, c11[2] = {0, 0};
     double*        st = sm.stage[warp];
 
-    for_each_item<K>(sm.S.tile[warp], cvL, cvG, sm.S.grid, sm.S.Rt, n_items, P.thr2,
-        [&](bool has, uint32_t pos, const float4& pl, double gx, double gy, double gz, float qx, float qy,
-            float qz, uint64_t (&key)[K]) {
+    for (uint32_t item = item_warp_id(); item < n_items; item += item_warp_count())
+    {
+        const uint32_t first = __ldg(cvL.item_first + item);
+        const uint32_t cnt = __ldg(cvL.item_first + item + 1) - first;
+        const bool     has = (uint32_t)lane < cnt;
+        const uint32_t pos = first + lane;
+        float4         pl = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has) pl = __ldg(cvL.pts + pos);
+        double gx, gy, gz;
+        transform_point(sm.Rt, pl, gx, gy, gz);
+        const float  qx = (float)gx, qy = (float)gy, qz = (float)gz;
         const double px = pl.x, py = pl.y, pz = pl.z;
         bool         paired = false;
         double       nrm[3] = {0, 0, 0}, r0 = 0;
         double       cen[3] = {0, 0, 0};
         if (has)
         {
+            uint32_t nb[K];
+            {
+                const uint2* row = reinterpret_cast<const uint2*>(nnj + (size_t)pos * K);
+#pragma unroll
+                for (int i = 0; i < K / 2; i++)
+                {
+                    const uint2 v = __ldg(row + i);
+                    nb[2 * i] = v.x, nb[2 * i + 1] = v.y;
+                }
+            }
             // neighbours kept after the distance cut; K may exceed the configured knn
             uint32_t m = 0;
 #pragma unroll
             for (int i = 0; i < K; i++)
-                if ((uint32_t)i < P.knn && key[i] != sent) m++;
+                if ((uint32_t)i < P.knn && nb[i] != kInvalid) m++;
 
             const uint32_t orig = __float_as_uint(pl.w);
             if (WRITE)
@@ -258,8 +466,7 @@ __global__ void __launch_bounds__(kChunk, 5)
 #pragma unroll
                     for (int i = 0; i < K; i++)
                         if ((uint32_t)i < P.knn)
-                            out.nn_idx[(size_t)orig * P.knn + i] =
-                                ((uint32_t)i < m) ? key_idx(key[i]) : kInvalid;
+                            out.nn_idx[(size_t)orig * P.knn + i] = ((uint32_t)i < m) ? nb[i] : kInvalid;
             }
 
             if (m >= P.min_plane_points && m > 0)
@@ -272,8 +479,8 @@ __global__ void __launch_bounds__(kChunk, 5)
                 for (int i = 0; i < K; i++)
                     if ((uint32_t)i < m)
                     {
-                        const uint32_t pos = __ldg(cvG.rank + key_idx(key[i]));
-                        const float4   pn = __ldg(cvG.pts + pos);
+                        const uint32_t np = __ldg(cvG.rank + nb[i]);
+                        const float4   pn = __ldg(cvG.pts + np);
                         nx_[i] = (double)pn.x, ny_[i] = (double)pn.y, nz_[i] = (double)pn.z;
                         sx += nx_[i], sy += ny_[i], sz += nz_[i];
                     }
@@ -339,9 +546,9 @@ __global__ void __launch_bounds__(kChunk, 5)
         }
         e[12] = r0, e[13] = f1, e[14] = 0.0, e[15] = 0.0;
         accumulate_moments(st, paired, e, c00, c01, c11);
-    });
+    }
 
-    write_cta_partial(reinterpret_cast<double*>(sm.S.tile), c00, c01, c11,
+    write_cta_partial(&sm.stage[0][0], c00, c01, c11,
                       partials + ((size_t)job * gridDim.x + blockIdx.x) * kNumMoments);
 }
 
@@ -350,12 +557,12 @@ __global__ void __launch_bounds__(kChunk, 5)
 // r = R p + t - q, linear in theta like the point-to-plane one:
 //   e = [ h (4) | r0 (3) | 0 ... ],  h = (p_local, 1)
 // so tile C00 holds sum h h^T, sum h r0^T, sum |r0|^2 (trace of the r0 block)
-// and the pairing count (S[3][3]).
+// and the pairing count (S[3][3]).  nn = [job base + sorted position][1].
 template <bool WRITE>
-__global__ void __launch_bounds__(kChunk, 5)
-    match_p2p_kernel(const CloudView* __restrict__ clouds, const JobDev* __restrict__ jobs,
-                     double* __restrict__ partials, IcpDevParams P, MatchOut out,
-                     PairRec* __restrict__ pairs)
+__global__ void __launch_bounds__(kChunk)
+    fit_p2p_kernel(const CloudView* __restrict__ clouds, const JobDev* __restrict__ jobs,
+                   const uint32_t* __restrict__ nn, double* __restrict__ partials, IcpDevParams P,
+                   MatchOut out, PairRec* __restrict__ pairs)
 {
     const uint32_t job = blockIdx.y;
     const JobDev&  J = jobs[job];
@@ -363,39 +570,44 @@ __global__ void __launch_bounds__(kChunk, 5)
     const CloudView cvL = clouds[J.to_cloud];
     const CloudView cvG = clouds[J.from_cloud];
     PairRec*        prec = pairs ? pairs + J.pair_base : nullptr;
+    const uint32_t* nnj = nn + (size_t)J.pair_base;
 
-    __shared__ MatchSmem sm;
-    const int tid = threadIdx.x, warp = tid >> 5;
-    if (tid < 12) sm.S.Rt[tid] = (tid < 9) ? J.R[tid] : J.t[tid - 9];
-    if (tid == 32) sm.S.grid = *cvG.grid;
-    if (tid == 64) sm.S.n_items = cvL.grid->n_items;
+    __shared__ FitSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 12) sm.Rt[tid] = (tid < 9) ? J.R[tid] : J.t[tid - 9];
+    if (tid == 32) sm.n_items = (cvG.grid->n_valid > 0) ? cvL.grid->n_items : 0u;
     __syncthreads();
-    const uint32_t it = J.iter;
-    const bool     active = (P.run_from_iteration <= it) &&
-                        (P.run_up_to_iteration == 0 || it <= P.run_up_to_iteration);
-    const uint32_t n_items = (active && sm.S.grid.n_valid > 0) ? sm.S.n_items : 0u;
-    const uint64_t sent = sentinel_key(P.thr2);
+    const uint32_t n_items = matcher_active(P, J.iter) ? sm.n_items : 0u;
     double         c00[2] = {0, 0}, c01[2] = {0, 0}, c11[2] = {0, 0};
     double*        st = sm.stage[warp];
 
-    for_each_item<1>(sm.S.tile[warp], cvL, cvG, sm.S.grid, sm.S.Rt, n_items, P.thr2,
-        [&](bool has, uint32_t pos, const float4& pl, double gx, double gy, double gz, float, float, float,
-            uint64_t (&key)[1]) {
+    for (uint32_t item = item_warp_id(); item < n_items; item += item_warp_count())
+    {
+        const uint32_t first = __ldg(cvL.item_first + item);
+        const uint32_t cnt = __ldg(cvL.item_first + item + 1) - first;
+        const bool     has = (uint32_t)lane < cnt;
+        const uint32_t pos = first + lane;
+        float4         pl = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has) pl = __ldg(cvL.pts + pos);
+        double gx, gy, gz;
+        transform_point(sm.Rt, pl, gx, gy, gz);
         bool   paired = false;
         double q[3] = {0, 0, 0};
         if (has)
         {
-            paired = (key[0] != sent) && (key_d2(key[0]) < P.thr2);
+            const uint32_t nb = __ldg(nnj + pos);
             const uint32_t orig = __float_as_uint(pl.w);
-            if (paired)
+            if (nb != kInvalid)
             {
-                const float4 pn = __ldg(cvG.pts + __ldg(cvG.rank + key_idx(key[0])));
-                q[0] = (double)pn.x, q[1] = (double)pn.y, q[2] = (double)pn.z;
+                const float4 pn = __ldg(cvG.pts + __ldg(cvG.rank + nb));
+                // the search keeps d2 <= thr^2; the matcher pairs d2 < thr^2
+                paired = dist2((float)gx, (float)gy, (float)gz, pn) < P.thr2;
+                if (paired) q[0] = (double)pn.x, q[1] = (double)pn.y, q[2] = (double)pn.z;
             }
             if (WRITE)
             {
                 if (out.nn_cnt) out.nn_cnt[orig] = paired ? 1u : 0u;
-                if (out.nn_idx) out.nn_idx[orig] = paired ? key_idx(key[0]) : kInvalid;
+                if (out.nn_idx) out.nn_idx[orig] = paired ? nb : kInvalid;
                 if (out.paired) out.paired[orig] = paired ? 1 : 0;
                 if (paired && out.centroid)
                     out.centroid[(size_t)orig * 3] = q[0], out.centroid[(size_t)orig * 3 + 1] = q[1],
@@ -415,8 +627,8 @@ __global__ void __launch_bounds__(kChunk, 5)
 #pragma unroll
         for (int i = 7; i < 16; i++) e[i] = 0.0;
         accumulate_moments(st, paired, e, c00, c01, c11);
-    });
-    write_cta_partial(reinterpret_cast<double*>(sm.S.tile), c00, c01, c11,
+    }
+    write_cta_partial(&sm.stage[0][0], c00, c01, c11,
                       partials + ((size_t)job * gridDim.x + blockIdx.x) * kNumMoments);
 }
 
@@ -507,6 +719,7 @@ __global__ void __launch_bounds__(kSolveThreads)
 {
     const uint32_t job = blockIdx.x;
     JobDev&        J = jobs[job];
+    if (threadIdx.x == 0) J.next_item = 0;  // the next search draws items from 0 again
     if (J.status != 0) return;
     const int tid = threadIdx.x, lane = tid & 31;
 
@@ -763,6 +976,7 @@ __global__ void __launch_bounds__(kSolveThreads)
 {
     const uint32_t job = blockIdx.x;
     JobDev&        J = jobs[job];
+    if (threadIdx.x == 0) J.next_item = 0;  // the next search draws items from 0 again
     if (J.status != 0) return;
     const int tid = threadIdx.x;
     __shared__ double sS[kNumMoments];
@@ -808,33 +1022,6 @@ __global__ void __launch_bounds__(kSolveThreads)
     mat3_vec(Tn.R, pc, Rp);
     for (int d = 0; d < 3; d++) Tn.t[d] = qc[d] - Rp[d];
     finish_outer_iteration(J, Tn, npair, 1u, P, n_active);
-}
-
-// ------------------------------------------------------------------ quality
-// QualityEvaluator_PairedRatio (row O / A.8): 1-NN within thresholdDistance.
-__global__ void __launch_bounds__(kChunk)
-    quality_kernel(const CloudView* __restrict__ clouds, JobDev* __restrict__ jobs, IcpDevParams P)
-{
-    const uint32_t  job = blockIdx.y;
-    JobDev&         J = jobs[job];
-    const CloudView cvL = clouds[J.to_cloud];
-    const CloudView cvG = clouds[J.from_cloud];
-    __shared__ SearchSmem sm;
-    const int tid = threadIdx.x;
-    if (tid < 12) sm.Rt[tid] = (tid < 9) ? J.R[tid] : J.t[tid - 9];
-    if (tid == 32) sm.grid = *cvG.grid;
-    if (tid == 64) sm.n_items = cvL.grid->n_items;
-    __syncthreads();
-    const uint32_t n_items = (sm.grid.n_valid > 0) ? sm.n_items : 0u;
-    const uint64_t sent = sentinel_key(P.q_thr2);
-    uint32_t       hits = 0;
-    for_each_item<1>(sm.tile[tid >> 5], cvL, cvG, sm.grid, sm.Rt, n_items, P.q_thr2,
-        [&](bool has, uint32_t, const float4&, double, double, double, float, float, float, uint64_t (&key)[1]) {
-            if (has && (key[0] != sent) && (key_d2(key[0]) < P.q_thr2)) hits++;  // strict
-        });
-    // integer count: any order gives the same sum
-    hits = __reduce_add_sync(0xFFFFFFFFu, hits);
-    if ((tid & 31) == 0 && hits) atomicAdd(&J.quality_count, hits);
 }
 
 // --------------------------------------------------------------- covariance
@@ -898,35 +1085,6 @@ __global__ void __launch_bounds__(64) covariance_kernel(JobDev* __restrict__ job
     }
 }
 
-// ---------------------------------------------------------------- kNN query
-template <int K>
-__global__ void __launch_bounds__(kChunk)
-    knn_kernel(CloudView cvG, CloudView cvL, Pose T, uint32_t k, float cap_d2,
-               uint32_t* __restrict__ idx_out, float* __restrict__ d2_out)
-{
-    __shared__ SearchSmem sm;
-    const int tid = threadIdx.x;
-    if (tid < 12) sm.Rt[tid] = (tid < 9) ? T.R[tid] : T.t[tid - 9];
-    if (tid == 32) sm.grid = *cvG.grid;
-    if (tid == 64) sm.n_items = cvL.grid->n_items;
-    __syncthreads();
-    const uint32_t n_items = (sm.grid.n_valid > 0) ? sm.n_items : 0u;
-    const uint64_t sent = sentinel_key(cap_d2);
-    for_each_item<K>(sm.tile[tid >> 5], cvL, cvG, sm.grid, sm.Rt, n_items, cap_d2,
-        [&](bool has, uint32_t, const float4& pl, double, double, double, float, float, float, uint64_t (&key)[K]) {
-            if (!has) return;
-            const uint32_t orig = __float_as_uint(pl.w);
-#pragma unroll
-            for (int i = 0; i < K; i++)
-                if ((uint32_t)i < k)
-                {
-                    const bool ok = key[i] != sent;
-                    idx_out[(size_t)orig * k + i] = ok ? key_idx(key[i]) : kInvalid;
-                    d2_out[(size_t)orig * k + i] = ok ? key_d2(key[i]) : INFINITY;
-                }
-        });
-}
-
 __global__ void fill_u32_kernel(uint32_t* p, size_t n, uint32_t v)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -937,6 +1095,38 @@ __global__ void fill_f32_kernel(float* p, size_t n, float v)
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
+__global__ void fill_u64_kernel(uint64_t* p, size_t n, uint64_t v)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// Arg-min merge of the partial results of disjoint map shards: one
+// thread per query takes the k smallest of `parts` ascending key lists.
+template <int K>
+__global__ void __launch_bounds__(256)
+    merge_keys_kernel(const uint64_t* __restrict__ parts, uint32_t nparts, size_t part_stride, size_t nq,
+                      uint32_t k, uint64_t* __restrict__ out)
+{
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    uint64_t key[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) key[i] = ~0ull;
+    for (uint32_t p = 0; p < nparts; p++)
+    {
+        const uint64_t* row = parts + (size_t)p * part_stride + q * k;
+        for (uint32_t i = 0; i < k; i++)
+        {
+            const uint64_t kk = __ldg(row + i);
+            if (!(kk < key[K - 1])) break;  // the lists are ascending
+            topk_insert<K>(key, kk);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < K; i++)
+        if ((uint32_t)i < k) out[q * k + i] = (key[i] == ~0ull) ? B200ICP_NO_KEY : key[i];
+}
 
 // =========================================================== host orchestration
 static int wait_cloud(Workspace* ws, const b200icp_cloud* c)
@@ -945,43 +1135,126 @@ static int wait_cloud(Workspace* ws, const b200icp_cloud* c)
     return B200ICP_OK;
 }
 
-// CTAs per job: every CTA walks the items c, c + G, ... of the local cloud.
-// Enough CTAs to fill the machine a few times over for one job, fewer per job
-// when many jobs share a launch (the partials buffer is G x 192 doubles per job).
-static uint32_t ctas_per_job(const ::b200icp* ctx, size_t max_points, size_t njobs)
+// Switches (environment, read once): B200ICP_SEARCH=sweep selects the tile
+// sweep (sweep_search.cuh) as the search stage instead of the per-lane shell
+// walk (tile_search.cuh; measured faster on LiDAR scans);
+// B200ICP_WPI=1|2|4 the warps that share one item in the sweep.
+struct SearchConfig
 {
-    // CTAs of the search kernels that are resident on one SM (registers and
-    // shared memory): one full wave for a single job, no ragged second wave
-    static int resident = 0;
-    if (resident == 0)
+    bool sweep = false;
+    int  wpi = 0;  // 0 = automatic
+};
+static const SearchConfig& search_config()
+{
+    static const SearchConfig cfg = [] {
+        SearchConfig c;
+        if (const char* s = getenv("B200ICP_SEARCH")) c.sweep = (strcmp(s, "sweep") == 0);
+        if (const char* w = getenv("B200ICP_WPI")) c.wpi = atoi(w);
+        return c;
+    }();
+    return cfg;
+}
+
+// CTAs per job of the FIT stage: every warp walks the items w, w + W, ... of
+// the local cloud.  Enough warps to fill the machine for one job, fewer per
+// job when many jobs share a launch (the partials buffer is G x 192 doubles
+// per job), and a warp count that gives every warp the same number of items.
+static uint32_t fit_ctas_per_job(const ::b200icp* ctx, size_t max_points, size_t njobs)
+{
+    const size_t items = std::max<size_t>(1, (max_points + kItem - 1) / kItem);
+    const size_t warps_per_cta = kChunk / 32;
+    size_t       max_warps = (size_t)ctx->sm_count * 16;  // 4 CTAs of 4 warps per SM
+    max_warps = std::max<size_t>(warps_per_cta * 2, (2 * max_warps + njobs - 1) / njobs);
+    max_warps = std::min<size_t>(max_warps, (size_t)ctx->sm_count * 16);
+    const size_t per_warp = (items + max_warps - 1) / max_warps;
+    const size_t warps = (items + per_warp - 1) / per_warp;
+    return (uint32_t)std::max<size_t>(1, (warps + warps_per_cta - 1) / warps_per_cta);
+}
+
+// search stage over a table of jobs: grid = (items of the largest local cloud, jobs)
+template <int K, class Epi>
+static void launch_search_k(const ::b200icp* ctx, Workspace* ws, size_t max_points, size_t njobs,
+                            const CloudView* d_clouds, JobDev* d_jobs, const IcpDevParams& D, float cap_d2,
+                            int gate, const Epi& epi)
+{
+    cudaStream_t        s = ws->stream;
+    const SearchConfig& cfg = search_config();
+    const size_t        items = std::max<size_t>(1, (max_points + kItem - 1) / kItem);
+    if (!cfg.sweep)
     {
-        int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, match_kernel<6, false>, kChunk, 0) != cudaSuccess ||
-            occ < 1)
-            occ = 4;
-        resident = occ;
+        // resident CTAs of the walk on one SM (registers and shared memory)
+        static int resident = 0;
+        if (resident == 0)
+        {
+            int occ = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_tile_kernel<6, NnWriter>, kChunk, 0) !=
+                    cudaSuccess || occ < 1)
+                occ = 4;
+            resident = occ;
+        }
+        const size_t   warps = kChunk / 32;
+        const size_t   wave = (size_t)ctx->sm_count * resident;
+        const size_t   cap = std::max<size_t>(4, (2 * wave + njobs - 1) / njobs);
+        const uint32_t G = (uint32_t)std::max<size_t>(1, std::min({(items + warps - 1) / warps, cap, wave}));
+        search_tile_kernel<K, Epi><<<dim3(G, (unsigned)njobs), kChunk, 0, s>>>(d_clouds, d_jobs, D, cap_d2, gate, epi);
     }
-    const size_t chunks = (max_points + kChunk - 1) / kChunk;
-    const size_t wave = (size_t)ctx->sm_count * resident;
-    size_t       cap = (2 * wave + njobs - 1) / njobs;
-    cap = std::max<size_t>(cap, 8);
-    cap = std::min<size_t>(cap, wave);
-    return (uint32_t)std::max<size_t>(1, std::min(2 * chunks, cap));
+    else
+    {
+        // one CTA per item up to a few waves per launch; more items are taken grid-stride
+        const size_t   budget = std::max<size_t>(64, ((size_t)ctx->sm_count * 64 + njobs - 1) / njobs);
+        const uint32_t G = (uint32_t)std::min(items, budget);
+        int            wpi = cfg.wpi;
+        if (wpi != 1 && wpi != 2 && wpi != 4) wpi = (items * njobs >= (size_t)ctx->sm_count * 256) ? 1 : 4;
+        const dim3 grid(G, (unsigned)njobs);
+        if (wpi == 1)
+            search_sweep_kernel<K, 1, Epi><<<grid, 32, 0, s>>>(d_clouds, d_jobs, D, cap_d2, gate, epi);
+        else if (wpi == 2)
+            search_sweep_kernel<K, 2, Epi><<<grid, 64, 0, s>>>(d_clouds, d_jobs, D, cap_d2, gate, epi);
+        else
+            search_sweep_kernel<K, 4, Epi><<<grid, 128, 0, s>>>(d_clouds, d_jobs, D, cap_d2, gate, epi);
+    }
+    ws->launches++;
+}
+
+// K of the matcher's search for the configured matcher / knn
+static int matcher_k(const IcpDevParams& D)
+{
+    if (D.matcher_kind == B200ICP_MATCHER_POINTS_DISTANCE) return 1;
+    return D.knn <= 4 ? 4 : (D.knn <= 6 ? 6 : 8);
+}
+
+// the matcher's search: neighbour rows [job base + sorted position][K]
+static void launch_match_search(const ::b200icp* ctx, Workspace* ws, size_t max_points, size_t njobs,
+                                const CloudView* d_clouds, JobDev* d_jobs, uint32_t* d_nn)
+{
+    const IcpDevParams& D = ctx->D;
+    const int           K = matcher_k(D);
+    const NnWriter      w = {d_nn, nullptr, (uint32_t)K, 0u};
+    if (K == 1)
+        launch_search_k<1>(ctx, ws, max_points, njobs, d_clouds, d_jobs, D, D.thr2, 1, w);
+    else if (K == 4)
+        launch_search_k<4>(ctx, ws, max_points, njobs, d_clouds, d_jobs, D, D.thr2, 1, w);
+    else if (K == 6)
+        launch_search_k<6>(ctx, ws, max_points, njobs, d_clouds, d_jobs, D, D.thr2, 1, w);
+    else
+        launch_search_k<8>(ctx, ws, max_points, njobs, d_clouds, d_jobs, D, D.thr2, 1, w);
 }
 
 template <bool WRITE>
-static void launch_match(Workspace* ws, const IcpDevParams& D, dim3 grid, const CloudView* d_clouds,
-                         const JobDev* d_jobs, double* d_partials, const MatchOut& mo, PairRec* d_pairs)
+static void launch_fit(Workspace* ws, const IcpDevParams& D, dim3 grid, const CloudView* d_clouds,
+                       const JobDev* d_jobs, const uint32_t* d_nn, double* d_partials, const MatchOut& mo,
+                       PairRec* d_pairs)
 {
     cudaStream_t s = ws->stream;
-    if (D.matcher_kind == B200ICP_MATCHER_POINTS_DISTANCE)
-        match_p2p_kernel<WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_partials, D, mo, d_pairs);
-    else if (D.knn == 6)
-        match_kernel<6, WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_partials, D, mo, d_pairs);
-    else if (D.knn <= 4)
-        match_kernel<4, WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_partials, D, mo, d_pairs);
+    const int    K = matcher_k(D);
+    if (K == 1)
+        fit_p2p_kernel<WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_nn, d_partials, D, mo, d_pairs);
+    else if (K == 4)
+        fit_plane_kernel<4, WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_nn, d_partials, D, mo, d_pairs);
+    else if (K == 6)
+        fit_plane_kernel<6, WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_nn, d_partials, D, mo, d_pairs);
     else
-        match_kernel<8, WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_partials, D, mo, d_pairs);
+        fit_plane_kernel<8, WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_nn, d_partials, D, mo, d_pairs);
     ws->launches++;
 }
 
@@ -1049,17 +1322,20 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
     }
     for (auto& kv : cmap)
         if (int r = wait_cloud(ws, kv.first)) return r;
-    const uint32_t G = ctas_per_job(ctx, max_points, n);
+    const uint32_t G = fit_ctas_per_job(ctx, max_points, n);
+    const int      K = matcher_k(D);
 
     const uint32_t GH = std::max<uint32_t>(1, std::min<uint32_t>(G, (uint32_t)((max_points + 1023) / 1024)));
     PairRec*       d_pairs = nullptr;
     double *       d_h0 = nullptr, *d_h1 = nullptr;
+    uint32_t*      d_nn = nullptr;
     Carver sz(nullptr);
     auto layout = [&](Carver& k, CloudView*& dc, JobDev*& dj, double*& dp, uint32_t*& da) {
         dc = k.take<CloudView>(views.size());
         dj = k.take<JobDev>(n);
         dp = k.take<double>((size_t)n * G * kNumMoments);
         da = k.take<uint32_t>(4);
+        d_nn = k.take<uint32_t>((total_queries ? total_queries : 1) * (size_t)K);
         if (horn)
         {
             d_pairs = k.take<PairRec>(total_queries ? total_queries : 1);
@@ -1107,8 +1383,9 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
         for (uint32_t i = 0; i < todo; i++, enq++)
         {
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 0], s));
-            launch_match<false>(ws, D, mgrid, d_clouds, d_jobs, d_partials, no_out, d_pairs);
+            launch_match_search(ctx, ws, max_points, n, d_clouds, d_jobs, d_nn);
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 1], s));
+            launch_fit<false>(ws, D, mgrid, d_clouds, d_jobs, d_nn, d_partials, no_out, d_pairs);
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 2], s));
             if (horn)
             {
@@ -1139,9 +1416,10 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
         }
         batch++;
     }
-    quality_kernel<<<mgrid, kChunk, 0, s>>>(d_clouds, d_jobs, D);
+    // QualityEvaluator_PairedRatio: one more search (k = 1, its own radius) on every job
+    launch_search_k<1>(ctx, ws, max_points, n, d_clouds, d_jobs, D, D.q_thr2, 0, HitCounter{D.q_thr2});
     covariance_kernel<<<(unsigned)n, 64, 0, s>>>(d_jobs, D);
-    ws->launches += 2;
+    ws->launches++;
     B2_CUDA_TRY(cudaMemcpyAsync(h_jobs, d_jobs, n * sizeof(JobDev), cudaMemcpyDeviceToHost, s));
     B2_CUDA_TRY(cudaStreamSynchronize(s));
     B2_CUDA_TRY(cudaGetLastError());
@@ -1168,19 +1446,22 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
     }
     if (prof)
     {
-        double mm = 0, sm = 0;
+        double mm = 0, fm = 0, sm = 0;
         for (uint32_t i = 0; i < std::min(max_runs, enq); i++)
         {
-            float a = 0, b = 0;
+            float a = 0, b = 0, c = 0;
             B2_CUDA_TRY(cudaEventElapsedTime(&a, ws->prof_ev[4 * i + 0], ws->prof_ev[4 * i + 1]));
+            B2_CUDA_TRY(cudaEventElapsedTime(&c, ws->prof_ev[4 * i + 1], ws->prof_ev[4 * i + 2]));
             B2_CUDA_TRY(cudaEventElapsedTime(&b, ws->prof_ev[4 * i + 2], ws->prof_ev[4 * i + 3]));
-            mm += a, sm += b;
+            mm += a, fm += c, sm += b;
         }
         std::lock_guard<std::mutex> lk(ctx->mtx);
         ctx->prof.match_launches += std::min(max_runs, enq);
         ctx->prof.match_ms += mm;
         // queries examined by those launches (single job: exact; batches: upper bound)
         ctx->prof.match_queries += (uint64_t)std::min(max_runs, enq) * total_queries;
+        ctx->prof.fit_launches += std::min(max_runs, enq);
+        ctx->prof.fit_ms += fm;
         ctx->prof.solve_launches += std::min(max_runs, enq);
         ctx->prof.solve_ms += sm;
     }
@@ -1194,11 +1475,15 @@ int run_align_batch(::b200icp* ctx, size_t n, const b200icp_cloud* const* from,
     if (n == 0) return B200ICP_OK;
     Lease L(ctx);
     if (!L.ws) return B200ICP_ERR_CUDA;
-    const size_t kWave = 32768;  // gridDim.y <= 65535
-    for (size_t i = 0; i < n; i += kWave)
+    // waves bound gridDim.y (<= 65535) and the neighbour buffer (K x 4 B per query)
+    const size_t kWaveJobs = 32768, kWaveQueries = (size_t)1 << 28;
+    for (size_t i = 0; i < n;)
     {
-        const size_t cnt = std::min(kWave, n - i);
+        size_t cnt = 0, queries = 0;
+        while (i + cnt < n && cnt < kWaveJobs && (cnt == 0 || queries + to[i + cnt]->n <= kWaveQueries))
+            queries += to[i + cnt]->n, cnt++;
         if (int r = run_wave(ctx, L.ws, cnt, from + i, to + i, guesses + 6 * i, out + i)) return r;
+        i += cnt;
     }
     return B200ICP_OK;
 }
@@ -1264,22 +1549,14 @@ int run_knn(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, co
     cudaStream_t s = ws->stream;
     const size_t nq = q->n;
     if (nq == 0) return B200ICP_OK;
-    if (int r = wait_cloud(ws, ref)) return r;
-    if (int r = wait_cloud(ws, q)) return r;
     uint32_t* d_idx = nullptr;
     float*    d_d2 = nullptr;
-    auto layout = [&](Carver& c) {
-        d_idx = c.take<uint32_t>(nq * k);
-        d_d2 = c.take<float>(nq * k);
-    };
-    Carver sz(nullptr);
-    layout(sz);
-    if (int r = ws->reserve_device(sz.off)) return r;
-    Carver real(ws->d_scratch);
-    layout(real);
-    Pose         T;
-    const double ident[6] = {0, 0, 0, 0, 0, 0};
-    pose_from_ypr(pose6 ? pose6 : ident, T);
+    SingleJob sj;
+    if (int r = single_job_setup(ws, ref, q, pose6, 0, sj, [&](Carver& c) {
+            d_idx = c.take<uint32_t>(nq * k);
+            d_d2 = c.take<float>(nq * k);
+        }))
+        return r;
     const float cap_d2 = max_dist * max_dist;
     const int   fb = (int)((nq * k + 255) / 256);
     fill_u32_kernel<<<fb, 256, 0, s>>>(d_idx, nq * k, kInvalid);
@@ -1291,19 +1568,47 @@ int run_knn(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, co
         if (int r = ws->reserve_prof_events(1)) return r;
         B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[0], s));
     }
-    const int       blocks = (int)ctas_per_job(ctx, nq, 1);
-    const CloudView vr = ref->view(), vq = q->view();
+    const NnWriter w = {d_idx, d_d2, k, 1u};
+    uint32_t*      d_dbg = nullptr;
+    const size_t   dbg_items = (nq + kItem - 1) / kItem + 1;
+    if (getenv("B200ICP_DBG_ITEMS"))
+    {
+        B2_CUDA_TRY(cudaMalloc(&d_dbg, dbg_items * sizeof(uint32_t)));
+        B2_CUDA_TRY(cudaMemset(d_dbg, 0, dbg_items * sizeof(uint32_t)));
+        B2_CUDA_TRY(cudaMemcpyToSymbol(g_dbg_item_cycles, &d_dbg, sizeof(d_dbg)));
+    }
     if (k == 1)
-        knn_kernel<1><<<blocks, kChunk, 0, s>>>(vr, vq, T, k, cap_d2, d_idx, d_d2);
+        launch_search_k<1>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
     else if (k <= 4)
-        knn_kernel<4><<<blocks, kChunk, 0, s>>>(vr, vq, T, k, cap_d2, d_idx, d_d2);
+        launch_search_k<4>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
     else if (k <= 6)
-        knn_kernel<6><<<blocks, kChunk, 0, s>>>(vr, vq, T, k, cap_d2, d_idx, d_d2);
+        launch_search_k<6>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
     else
-        knn_kernel<8><<<blocks, kChunk, 0, s>>>(vr, vq, T, k, cap_d2, d_idx, d_d2);
-    ws->launches++;
+        launch_search_k<8>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
     if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[1], s));
     B2_CUDA_TRY(cudaGetLastError());
+    if (d_dbg)
+    {
+        std::vector<uint32_t> h(dbg_items);
+        B2_CUDA_TRY(cudaMemcpy(h.data(), d_dbg, dbg_items * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        uint32_t* null_ptr = nullptr;
+        B2_CUDA_TRY(cudaMemcpyToSymbol(g_dbg_item_cycles, &null_ptr, sizeof(null_ptr)));
+        cudaFree(d_dbg);
+        std::vector<uint32_t> tiled, fb;
+        for (uint32_t v : h)
+            if (v) ((v & 0x80000000u) ? fb : tiled).push_back(v & 0x7FFFFFFFu);
+        auto stats = [](std::vector<uint32_t>& v, const char* name) {
+            if (v.empty()) { fprintf(stderr, "[dbg items] %s: none\n", name); return; }
+            std::sort(v.begin(), v.end());
+            double sum = 0;
+            for (uint32_t x : v) sum += x;
+            fprintf(stderr, "[dbg items] %s: n=%zu cycles mean=%.0f p50=%u p90=%u p99=%u max=%u sum=%.3g\n", name,
+                    v.size(), sum / v.size(), v[v.size() / 2], v[v.size() * 9 / 10], v[v.size() * 99 / 100],
+                    v.back(), sum);
+        };
+        stats(tiled, "tiled");
+        stats(fb, "fallback");
+    }
     if (idx_out)
         B2_CUDA_TRY(cudaMemcpyAsync(idx_out, d_idx, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     if (d2_out)
@@ -1321,6 +1626,82 @@ int run_knn(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, co
     return B200ICP_OK;
 }
 
+int run_knn_keys(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, const double* pose6,
+                 uint32_t k, float max_dist, const uint32_t* d_index_map, uint64_t* d_keys_out)
+{
+    if (k < 1 || k > B200ICP_MAX_KNN || !(max_dist > 0) || !std::isfinite(max_dist))
+    {
+        set_error("k=%u outside [1,%d] or max_dist not positive and finite", k, B200ICP_MAX_KNN);
+        return B200ICP_ERR_BAD_ARG;
+    }
+    Lease L(ctx);
+    if (!L.ws) return B200ICP_ERR_CUDA;
+    Workspace*   ws = L.ws;
+    cudaStream_t s = ws->stream;
+    const size_t nq = q->n;
+    if (nq == 0) return B200ICP_OK;
+    SingleJob sj;
+    if (int r = single_job_setup(ws, ref, q, pose6, 0, sj, [&](Carver&) {})) return r;
+    const float cap_d2 = max_dist * max_dist;
+    fill_u64_kernel<<<(int)((nq * k + 255) / 256), 256, 0, s>>>(d_keys_out, nq * k, B200ICP_NO_KEY);
+    ws->launches++;
+    const bool prof = ctx->profile_on;
+    if (prof)
+    {
+        if (int r = ws->reserve_prof_events(1)) return r;
+        B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[0], s));
+    }
+    const KeyWriter w = {d_keys_out, d_index_map, k};
+    if (k == 1)
+        launch_search_k<1>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
+    else if (k <= 4)
+        launch_search_k<4>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
+    else if (k <= 6)
+        launch_search_k<6>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
+    else
+        launch_search_k<8>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
+    if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[1], s));
+    B2_CUDA_TRY(cudaGetLastError());
+    B2_CUDA_TRY(cudaStreamSynchronize(s));
+    if (prof)
+    {
+        float ms = 0;
+        B2_CUDA_TRY(cudaEventElapsedTime(&ms, ws->prof_ev[0], ws->prof_ev[1]));
+        std::lock_guard<std::mutex> lk(ctx->mtx);
+        ctx->prof.knn_launches++;
+        ctx->prof.knn_ms += ms;
+        ctx->prof.knn_queries += nq;
+    }
+    return B200ICP_OK;
+}
+
+int run_merge_keys(::b200icp* ctx, const uint64_t* d_parts, uint32_t parts, size_t part_stride, size_t nq,
+                   uint32_t k, uint64_t* d_out)
+{
+    if (k < 1 || k > B200ICP_MAX_KNN)
+    {
+        set_error("k=%u outside [1,%d]", k, B200ICP_MAX_KNN);
+        return B200ICP_ERR_BAD_ARG;
+    }
+    if (nq == 0) return B200ICP_OK;
+    Lease L(ctx);
+    if (!L.ws) return B200ICP_ERR_CUDA;
+    cudaStream_t s = L.ws->stream;
+    const int    blocks = (int)((nq + 255) / 256);
+    if (k == 1)
+        merge_keys_kernel<1><<<blocks, 256, 0, s>>>(d_parts, parts, part_stride, nq, k, d_out);
+    else if (k <= 4)
+        merge_keys_kernel<4><<<blocks, 256, 0, s>>>(d_parts, parts, part_stride, nq, k, d_out);
+    else if (k <= 6)
+        merge_keys_kernel<6><<<blocks, 256, 0, s>>>(d_parts, parts, part_stride, nq, k, d_out);
+    else
+        merge_keys_kernel<8><<<blocks, 256, 0, s>>>(d_parts, parts, part_stride, nq, k, d_out);
+    L.ws->launches++;
+    B2_CUDA_TRY(cudaGetLastError());
+    B2_CUDA_TRY(cudaStreamSynchronize(s));
+    return B200ICP_OK;
+}
+
 int run_match(::b200icp* ctx, const b200icp_cloud* from, const b200icp_cloud* to,
               const double* pose6, uint8_t* paired, uint32_t* nn_idx, uint32_t* nn_cnt,
               double* centroid, double* normal, uint32_t* n_pairings)
@@ -1334,13 +1715,15 @@ int run_match(::b200icp* ctx, const b200icp_cloud* from, const b200icp_cloud* to
     const size_t        n = to->n, k = (D.matcher_kind == B200ICP_MATCHER_POINTS_DISTANCE) ? 1 : D.knn;
     if (n_pairings) *n_pairings = 0;
     if (n == 0) return B200ICP_OK;
-    const uint32_t G = ctas_per_job(ctx, n, 1);
+    const uint32_t G = fit_ctas_per_job(ctx, n, 1);
     double*        d_partials = nullptr;
+    uint32_t*      d_nn = nullptr;
     MatchOut       mo;
     SingleJob      sj;
     // the matcher is active at iteration run_from_iteration
     if (int r = single_job_setup(ws, from, to, pose6, D.run_from_iteration, sj, [&](Carver& c) {
             d_partials = c.take<double>((size_t)G * kNumMoments);
+            d_nn = c.take<uint32_t>(n * (size_t)matcher_k(D));
             mo.paired = c.take<uint8_t>(n);
             mo.nn_idx = c.take<uint32_t>(n * k);
             mo.nn_cnt = c.take<uint32_t>(n);
@@ -1353,7 +1736,8 @@ int run_match(::b200icp* ctx, const b200icp_cloud* from, const b200icp_cloud* to
     B2_CUDA_TRY(cudaMemsetAsync(mo.nn_idx, 0xFF, n * k * sizeof(uint32_t), s));
     B2_CUDA_TRY(cudaMemsetAsync(mo.centroid, 0, n * 3 * sizeof(double), s));
     B2_CUDA_TRY(cudaMemsetAsync(mo.normal, 0, n * 3 * sizeof(double), s));
-    launch_match<true>(ws, D, dim3(G, 1), sj.d_clouds, sj.d_jobs, d_partials, mo, nullptr);
+    launch_match_search(ctx, ws, n, 1, sj.d_clouds, sj.d_jobs, d_nn);
+    launch_fit<true>(ws, D, dim3(G, 1), sj.d_clouds, sj.d_jobs, d_nn, d_partials, mo, nullptr);
     B2_CUDA_TRY(cudaGetLastError());
     std::vector<double> part((size_t)G * kNumMoments);
     B2_CUDA_TRY(cudaMemcpyAsync(part.data(), d_partials, part.size() * sizeof(double),

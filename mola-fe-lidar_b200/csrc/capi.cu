@@ -83,6 +83,12 @@ extern "C" void b200icp_destroy(b200icp_t* icp)
         w->destroy();
         delete w;
     }
+    {
+        std::lock_guard<std::mutex> lk(icp->mtx);
+        icp->drain_pending();
+        for (auto e : icp->event_pool) cudaEventDestroy(e);
+        icp->event_pool.clear();
+    }
     delete icp;
 }
 
@@ -221,6 +227,29 @@ extern "C" int b200icp_knn(b200icp_t* icp, const b200icp_cloud_t* ref, const b20
     return run_knn(icp, ref, queries, pose6, k, max_dist, idx_out, d2_out);
 }
 
+extern "C" int b200icp_knn_keys_device(b200icp_t* icp, const b200icp_cloud_t* ref,
+                                       const b200icp_cloud_t* queries, const double* pose6, uint32_t k,
+                                       float max_dist, const uint32_t* d_index_map, uint64_t* d_keys_out)
+{
+    if (!icp || !ref || !queries || !d_keys_out)
+    {
+        set_error("null argument");
+        return B200ICP_ERR_BAD_ARG;
+    }
+    return run_knn_keys(icp, ref, queries, pose6, k, max_dist, d_index_map, d_keys_out);
+}
+
+extern "C" int b200icp_merge_keys_device(b200icp_t* icp, const uint64_t* d_parts, uint32_t parts,
+                                         size_t part_stride, size_t nq, uint32_t k, uint64_t* d_out)
+{
+    if (!icp || !d_parts || !d_out || parts == 0)
+    {
+        set_error("null argument");
+        return B200ICP_ERR_BAD_ARG;
+    }
+    return run_merge_keys(icp, d_parts, parts, part_stride, nq, k, d_out);
+}
+
 extern "C" int b200icp_match(b200icp_t* icp, const b200icp_cloud_t* from_global,
                              const b200icp_cloud_t* to_local, const double* pose6, uint8_t* paired,
                              uint32_t* nn_idx, uint32_t* nn_cnt, double* centroid, double* normal,
@@ -275,12 +304,14 @@ extern "C" void b200icp_profile_reset(b200icp_t* icp)
 {
     if (!icp) return;
     std::lock_guard<std::mutex> lk(icp->mtx);
+    icp->drain_pending();
     memset(&icp->prof, 0, sizeof(icp->prof));
 }
 extern "C" void b200icp_profile_get(b200icp_t* icp, b200icp_profile_t* out)
 {
     if (!icp || !out) return;
     std::lock_guard<std::mutex> lk(icp->mtx);
+    icp->drain_pending();
     *out = icp->prof;
 }
 extern "C" int b200icp_synchronize(b200icp_t* icp)

@@ -202,7 +202,7 @@ __global__ void fine_publish_kernel(const unsigned long long* __restrict__ skeys
                                     const unsigned long long* __restrict__ flags,
                                     const unsigned long long* __restrict__ ords,
                                     const uint32_t* __restrict__ hkeys, uint4* __restrict__ hrecs,
-                                    uint32_t hshift, uint32_t hmask,
+                                    uint2* __restrict__ hrange, uint32_t hshift, uint32_t hmask,
                                     uint32_t* __restrict__ fine_start,
                                     uint32_t* __restrict__ item_first, GridDev* __restrict__ g)
 {
@@ -224,11 +224,17 @@ __global__ void fine_publish_kernel(const unsigned long long* __restrict__ skeys
         g->n_items = items;
     }
     if (item_flag) item_first[item_ord] = j;
-    if (!fine_flag) return;
-    fine_start[fine_ord] = j;
+    // the last point of every block publishes the block's end, the first its start
+    const bool blk_last = last || ((skeys[j + 1] >> 6) != (key >> 6));
+    const bool blk_first = (j == 0) || ((skeys[j - 1] >> 6) != (key >> 6));
+    if (!fine_flag && !blk_last) return;
     const uint32_t bkey = block_key_of(key);
     uint32_t       slot = hash_slot(bkey, hshift);
     while (hkeys[slot] != bkey) slot = (slot + 1) & hmask;
+    if (blk_last) hrange[slot].y = j + 1;
+    if (blk_first) hrange[slot].x = j;
+    if (!fine_flag) return;
+    fine_start[fine_ord] = j;
     unsigned long long* mask = reinterpret_cast<unsigned long long*>(&hrecs[slot].z);
     atomicOr(mask, 1ull << (uint32_t)(key & 63ull));
 }
@@ -260,6 +266,7 @@ int cloud_alloc(::b200icp* ctx, Workspace* ws, size_t n, float search_radius, b2
         c->rank = k.take<uint32_t>(nn);
         c->hkeys = k.take<uint32_t>(cap);
         c->hrecs = k.take<uint4>(cap);
+        c->hrange = k.take<uint2>(cap);
         c->fine_start = k.take<uint32_t>(nn + 1);
         c->item_first = k.take<uint32_t>(nn + 1);
         c->grid = k.take<GridDev>(1);
@@ -292,10 +299,23 @@ int cloud_build_index(::b200icp* ctx, Workspace* ws, b200icp_cloud* c)
     cudaStream_t   s = ws->stream;
     const uint32_t n = (uint32_t)c->n;
     const bool     prof = ctx->profile_on;
+    cudaEvent_t    pe0 = nullptr, pe1 = nullptr;
     if (prof)
     {
-        if (int r = ws->reserve_prof_events(1)) return r;
-        B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[0], s));
+        {
+            std::lock_guard<std::mutex> lk(ctx->mtx);
+            if (ctx->event_pool.size() >= 2)
+            {
+                pe0 = ctx->event_pool.back(), ctx->event_pool.pop_back();
+                pe1 = ctx->event_pool.back(), ctx->event_pool.pop_back();
+            }
+        }
+        if (!pe0)
+        {
+            B2_CUDA_TRY(cudaEventCreate(&pe0));
+            B2_CUDA_TRY(cudaEventCreate(&pe1));
+        }
+        B2_CUDA_TRY(cudaEventRecord(pe0, s));
     }
     // identities for the atomic min / max, empty hash
     B2_CUDA_TRY(cudaMemsetAsync(c->bbox_enc, 0xFF, 3 * sizeof(uint32_t), s));
@@ -343,7 +363,7 @@ int cloud_build_index(::b200icp* ctx, Workspace* ws, b200icp_cloud* c)
         block_insert_kernel<<<blocks, 256, 0, s>>>(keys.Current(), n, ford, c->hkeys, c->hrecs,
                                                    c->hshift, c->hcap - 1, c->grid);
         fine_publish_kernel<<<blocks, 256, 0, s>>>(keys.Current(), n, fflag, ford, c->hkeys, c->hrecs,
-                                                   c->hshift, c->hcap - 1, c->fine_start,
+                                                   c->hrange, c->hshift, c->hcap - 1, c->fine_start,
                                                    c->item_first, c->grid);
         ws->launches += 4 + 6 + 2;  // ours + radix sort passes + scan
     }
@@ -351,14 +371,10 @@ int cloud_build_index(::b200icp* ctx, Workspace* ws, b200icp_cloud* c)
     B2_CUDA_TRY(cudaEventRecord(c->ready, s));
     if (prof)
     {
-        B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[1], s));
-        B2_CUDA_TRY(cudaEventSynchronize(ws->prof_ev[1]));
-        float ms = 0;
-        B2_CUDA_TRY(cudaEventElapsedTime(&ms, ws->prof_ev[0], ws->prof_ev[1]));
+        B2_CUDA_TRY(cudaEventRecord(pe1, s));
         std::lock_guard<std::mutex> lk(ctx->mtx);
-        ctx->prof.index_builds++;
-        ctx->prof.index_ms += ms;
-        ctx->prof.index_points += n;
+        ctx->pending_index.push_back({pe0, pe1, n});
+        if (ctx->pending_index.size() > 4096) ctx->drain_pending();
     }
     return B200ICP_OK;
 }

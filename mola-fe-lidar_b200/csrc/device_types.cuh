@@ -7,9 +7,10 @@
 //                         (30-bit Morton code of the point's BLOCK, 6-bit fine
 //                         cell inside the block)
 //   rank[n]               original index -> sorted position
-//   hkeys/hrecs           open-addressing hash: linear block key -> BlockRec
+//   hkeys/hrecs/hrange    open-addressing hash: linear block key -> BlockRec
 //                         {first point, first fine-cell ordinal, 64-bit
-//                         occupancy mask of its 4x4x4 fine cells}
+//                         occupancy mask of its 4x4x4 fine cells} and the
+//                         block's point range [first, end) for the tile sweep
 //   fine_start[n_fine+1]  first point of every occupied fine cell, in order
 //   item_first[n_items+1] work items of the cloud when it is the LOCAL (query)
 //                         side: runs of kItem consecutive sorted points:
@@ -54,6 +55,7 @@ struct CloudView
     const GridDev*  grid;
     const uint32_t* hkeys;
     const uint4*    hrecs;       // BlockRec as (start, fine_base, mask.lo, mask.hi)
+    const uint2*    hrange;      // [first, last+1) sorted positions of the block's points
     const uint32_t* fine_start;
     const uint32_t* item_first;
     uint32_t        hshift;  // 32 - log2(capacity)
@@ -76,7 +78,9 @@ struct JobDev
     uint32_t cov_singular;
     uint32_t from_cloud, to_cloud;  // indices into the launch's CloudView table
     uint32_t inner_iters_total;
-    uint32_t pair_base;    // first PairRec of this job in the launch's pair buffer (Horn)
+    uint32_t pair_base;    // first row of this job in the launch's neighbour / pair buffers
+    uint32_t next_item;    // work counter of the search stage (reset by the solver)
+    uint32_t pad_;
 };
 
 struct IcpDevParams

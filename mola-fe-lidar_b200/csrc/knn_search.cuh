@@ -16,6 +16,10 @@
 #pragma once
 #include "device_types.cuh"
 
+#ifndef B200ICP_SCAN8
+#define B200ICP_SCAN8 1
+#endif
+
 namespace b2
 {
 __device__ __forceinline__ uint64_t make_key(float d2, uint32_t idx)
@@ -110,6 +114,30 @@ __device__ __forceinline__ void scan_range(const float4* __restrict__ pts, uint3
                                            uint64_t (&key)[K])
 {
     uint32_t j = beg;
+#if B200ICP_SCAN8
+    for (; j + 8 <= end; j += 8)
+    {
+        // long runs (dense cells) are latency bound: eight independent loads in flight
+        float4 c[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) c[u] = __ldg(pts + j + u);
+        uint64_t kk[8];
+        bool     any = false;
+        const uint64_t w = key[K - 1];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+        {
+            kk[u] = make_key(dist2(qx, qy, qz, c[u]), __float_as_uint(c[u].w));
+            any |= kk[u] < w;
+        }
+        if (any)
+        {
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (kk[u] < key[K - 1]) topk_insert<K>(key, kk[u]);
+        }
+    }
+#endif
     for (; j + 4 <= end; j += 4)
     {
         // four independent loads in flight before the first use

@@ -131,6 +131,23 @@ b2::Workspace* b200icp::acquire()
     return w;
 }
 
+void b200icp::drain_pending()
+{
+    for (auto& p : pending_index)
+    {
+        float ms = 0;
+        if (cudaEventSynchronize(p.e1) == cudaSuccess && cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess)
+        {
+            prof.index_builds++;
+            prof.index_ms += ms;
+            prof.index_points += p.points;
+        }
+        event_pool.push_back(p.e0);
+        event_pool.push_back(p.e1);
+    }
+    pending_index.clear();
+}
+
 void b200icp::release(b2::Workspace* ws)
 {
     std::lock_guard<std::mutex> lk(mtx);

@@ -80,6 +80,16 @@ struct b200icp
     bool                               profile_on = false;
     b200icp_profile_t                  prof;
     int                                sm_count = 148;
+    // index-build timings are resolved lazily (profile_get / reset) so that
+    // profiling adds no host synchronisation to the upload path
+    struct PendingIndexTime
+    {
+        cudaEvent_t e0, e1;
+        uint64_t    points;
+    };
+    std::vector<PendingIndexTime> pending_index;
+    std::vector<cudaEvent_t>      event_pool;
+    void                          drain_pending();  // call with mtx held
 
     b2::Workspace* acquire();
     void                release(b2::Workspace* ws);
@@ -95,6 +105,7 @@ struct b200icp_cloud
     uint32_t* rank = nullptr;
     uint32_t* hkeys = nullptr;
     uint4*    hrecs = nullptr;
+    uint2*    hrange = nullptr;
     uint32_t* fine_start = nullptr;
     uint32_t* item_first = nullptr;
     b2::GridDev* grid = nullptr;
@@ -106,7 +117,7 @@ struct b200icp_cloud
     b2::CloudView view() const
     {
         b2::CloudView v;
-        v.pts = pts, v.rank = rank, v.grid = grid, v.hkeys = hkeys, v.hrecs = hrecs;
+        v.pts = pts, v.rank = rank, v.grid = grid, v.hkeys = hkeys, v.hrecs = hrecs, v.hrange = hrange;
         v.fine_start = fine_start;
         v.item_first = item_first;
         v.hshift = hshift, v.hmask = hcap - 1, v.n = (uint32_t)n;
@@ -135,6 +146,10 @@ int run_align_batch(::b200icp* ctx, size_t n, const b200icp_cloud* const* from,
                     const b200icp_cloud* const* to, const double* guesses, b200icp_result_t* out);
 int run_knn(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, const double* pose6,
             uint32_t k, float max_dist, uint32_t* idx_out, float* d2_out);
+int run_knn_keys(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, const double* pose6,
+                 uint32_t k, float max_dist, const uint32_t* d_index_map, uint64_t* d_keys_out);
+int run_merge_keys(::b200icp* ctx, const uint64_t* d_parts, uint32_t parts, size_t part_stride, size_t nq,
+                   uint32_t k, uint64_t* d_out);
 int run_match(::b200icp* ctx, const b200icp_cloud* from, const b200icp_cloud* to,
               const double* pose6, uint8_t* paired, uint32_t* nn_idx, uint32_t* nn_cnt,
               double* centroid, double* normal, uint32_t* n_pairings);

@@ -129,6 +129,7 @@ void LidarOdometry::initialize(const Yaml& c)
     cfg.load_opt("viz_decor_pointsize", params_.viz_decor_pointsize);
     // additive keys of this implementation
     cfg.load_opt("b200_device", params_.device);
+    cfg.load_opt("b200_extra_edge_checks", params_.extra_edge_checks);
     {
         unsigned int seed = (unsigned int)params_.montecarlo_seed;
         cfg.load_opt("b200_montecarlo_seed", seed);
@@ -375,7 +376,7 @@ void LidarOdometry::doProcessNewObservation(CObservation::Ptr& o)
             std::lock_guard<std::mutex> lck(local_pose_graph_mtx);
             can_check_for_other_matches = !state_.local_pose_graph.graph.edges.empty();
         }
-        if (can_check_for_other_matches)
+        if (can_check_for_other_matches && params_.extra_edge_checks)
         {
             ProfilerEntry tle(profiler_, "doProcessNewObservation.6.checkForNearbyKFs");
             checkForNearbyKFs();

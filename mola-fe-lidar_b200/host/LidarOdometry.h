@@ -124,6 +124,10 @@ class LidarOdometry : public FrontEndBase
          *  an unseeded generator, cpp:773) */
         uint64_t montecarlo_seed{1};
         int      device{0};
+        /** additive key `b200_extra_edge_checks`: false skips checkForNearbyKFs
+         *  (cpp:493-508), so that every processed scan costs exactly one
+         *  consecutive-scan registration (the unit bench.py times) */
+        bool extra_edge_checks{true};
     };
     Parameters params_;
 

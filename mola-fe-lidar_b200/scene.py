@@ -68,7 +68,7 @@ class World:
             cy = rng.choice((-1.0, 1.0)) * rng.uniform(2.8, 3.8)
             boxes.append((cx - 2.2, cy - 0.9, GROUND_Z, cx + 2.2, cy + 0.9, GROUND_Z + 1.5))
         # boundary walls: every ray hits something
-        L, H, T = half_length, 60.0, 2.0
+        L, H, T = half_length, 100.0, 2.0  # tall enough for the +15 deg beams of the 128-beam sensor
         boxes += [(L, -L - T, GROUND_Z, L + T, L + T, H), (-L - T, -L - T, GROUND_Z, -L, L + T, H),
                   (-L, L, GROUND_Z, L, L + T, H), (-L, -L - T, GROUND_Z, L, -L, H)]
         self.boxes = np.array(boxes, dtype=np.float64)

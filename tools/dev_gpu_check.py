@@ -43,9 +43,10 @@ def main():
             dt = time.time() - t
         p = icp.profile()
         gt = scene.relative_pose6(poses[i - 1], poses[i])
-        print("align %d: wall %.2f ms iters=%d term=%s pairs=%d q=%.3f | match avg %.3f ms x%d, solve avg %.3f ms | err %s" %
+        print("align %d: wall %.2f ms iters=%d term=%s pairs=%d q=%.3f | search avg %.3f ms x%d, fit avg %.3f ms, solve avg %.3f ms | err %s" %
               (i, dt * 1e3, r["n_iterations"], capi.TERM[r["termination_reason"]], r["n_pairings"],
                r["quality"], p["match_ms"] / max(p["match_launches"], 1), p["match_launches"],
+               p["fit_ms"] / max(p["fit_launches"], 1),
                p["solve_ms"] / max(p["solve_launches"], 1), np.round(r["pose"] - gt, 4)))
         icp.profile_reset()
     icp.profile_enable(False)

@@ -19,8 +19,8 @@ CUDA-event timing, max over ranks):
                  Monte-Carlo guesses, pairs sharded i -> rank i mod N,
   `sharded_knn`  config C5's shape: a 128-beam scan against a map split by
                  spatial cell over the N GPUs, partial arg-min keys merged over
-                 NCCL (all-reduce MIN for k=1; all-to-all + merge kernel +
-                 all-gather for k=6).
+                 NCCL (all-reduce MIN for k=1; all-gather + k-way merge kernel
+                 for k=6).
 `--impl reference` times the CPU oracle port (the reference's own ICP cannot
 be built here) on all host threads, rank 0 only.
 """
@@ -333,15 +333,21 @@ def sharded_knn(torch, dist, capi, scans, poses, rank, world, local_rank, dev, m
         sm.query(qc, k, 0.7)
         if dist is not None:
             dist.barrier()
+        icp.profile_enable(True)
+        icp.profile_reset()
         ms, keys = timed(torch, lambda: [sm.query(qc, k, 0.7) for _ in range(3)][-1])
         ms /= 3
+        pr = icp.profile()
+        icp.profile_enable(False)
+        search_ms = pr["knn_ms"] / max(pr["knn_launches"], 1)
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         found = int((keys != M.NO_KEY).sum().item())
         out["cases"].append({"k": k, "radius_m": 0.7, "ms": float(t[0]), "queries_per_s": len(queries) / (float(t[0]) * 1e-3),
                              "neighbours_found": found, "exchange_bytes_per_rank": int(sm.last_exchange_bytes),
-                             "merge": "all_reduce(MIN, int64)" if k == 1 else "all_to_all + merge kernel + all_gather"})
+                             "merge": "all_reduce(MIN, int64)" if k == 1 else "all_gather + k-way merge kernel",
+                             "search_kernel_ms_rank0": search_ms})
     qc.free()
     search.close()
     icp.close()
@@ -426,7 +432,9 @@ def run_b200(args, rank, world, local_rank):
     # exactly one consecutive-scan registration -- the unit `value` and the
     # reference arm count; `e2e_full_module` below runs the module as shipped.
     def run_module(extra_yaml, steps, warm):
-        lo = lidar_odometry.LidarOdometry(yaml_text=lidar_odometry.system_yaml(extra=extra_yaml))
+        # additive key b200_device: this rank's GPU
+        lo = lidar_odometry.LidarOdometry(
+            yaml_text=lidar_odometry.system_yaml(extra=f"  b200_device: {local_rank}\n" + extra_yaml))
         stamp = 0.0
         for s in range(warm + 1):  # +1: the first scan only creates a keyframe
             h = hscans[scan_index(s)]
@@ -449,9 +457,9 @@ def run_b200(args, rank, world, local_rank):
         prof_mod = lo.profile()
         lo.close()
         n_all = max(st["n_processed"], 1)
-        sections = {k.replace("doProcessNewObservation.", ""): round(v[1] / max(v[0], 1) * 1e3, 4)
-                    for k, v in prof_mod.items() if v[0] > 0 and not k.startswith("exception")}
-        log(f"[bench] module sections, mean ms per call over {n_all} scans:", json.dumps(sections))
+        sections = {k.replace("doProcessNewObservation.", ""): [round(v[1] / max(v[0], 1) * 1e3, 3), round(v[2] * 1e3, 3)]
+                    for k, v in prof_mod.items() if v[0] > 0 and not k.startswith("exception") and v[1] > 1e-5}
+        log(f"[bench] module sections, [mean, max] ms per call over {n_all} scans:", json.dumps(sections))
         return ms, int(st["n_icp"] - st0["n_icp"]), int(st["n_processed"] - st0["n_processed"]), \
             int(st["n_keyframes"])
 

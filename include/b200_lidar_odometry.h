@@ -66,7 +66,7 @@ int  b200lo_get_state(b200lo_t* lo, b200lo_state_t* out);
 size_t b200lo_get_factors(b200lo_t* lo, b200lo_factor_t* out, size_t cap);
 /* the scalar front-end parameters after YAML loading, as "key=value\n" text */
 size_t b200lo_dump_params(b200lo_t* lo, char* buf, size_t cap);
-/* profiler sections (name, count, total seconds) as "name,count,total\n" */
+/* profiler sections (name, count, total seconds, longest call) as "name,count,total,max\n" */
 size_t b200lo_dump_profile(b200lo_t* lo, char* buf, size_t cap);
 /* raw handle of the ICP object of one AlignKind (0,1,2) for profiling hooks */
 void* b200lo_icp_handle(b200lo_t* lo, int align_kind);

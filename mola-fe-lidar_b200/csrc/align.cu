@@ -300,6 +300,16 @@ __device__ __forceinline__ void for_each_item(WarpTile& W, const CloudView& cvL,
         f(has, first + lane, __float_as_uint(pl.w), key);
         if (g_dbg_item_cycles && lane == 0)
             g_dbg_item_cycles[item] = (uint32_t)min((long long)0x7FFFFFFF, clock64() - dbg_t0) | (tiled ? 0u : 0x80000000u);
+#ifdef B200ICP_DBG_COUNT
+        if (g_dbg_lane_cand && g_dbg_item_cycles)
+        {   // per item: max and sum over lanes of the candidates scanned
+            uint32_t* slot = g_dbg_lane_cand + (blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+            const uint32_t c = *slot;
+            *slot = 0;
+            const uint32_t mx = __reduce_max_sync(0xFFFFFFFFu, c), sm = __reduce_add_sync(0xFFFFFFFFu, c);
+            if (lane == 0) g_dbg_item_cycles[n_items + 1 + 2 * item] = mx, g_dbg_item_cycles[n_items + 2 + 2 * item] = sm;
+        }
+#endif
     }
 }
 
@@ -403,7 +413,7 @@ static_assert(16 * kStageStride >= kNumMoments, "the stage buffers double as the
 // summation order of the moments never depends on scheduling).
 // grid = (CTAs per job, jobs).  nn = [job base + sorted position][K].
 template <int K, bool WRITE>
-__global__ void __launch_bounds__(kChunk)
+__global__ void __launch_bounds__(kChunk, 4)
     fit_plane_kernel(const CloudView* __restrict__ clouds, const JobDev* __restrict__ jobs,
                      const uint32_t* __restrict__ nn, double* __restrict__ partials, IcpDevParams P,
                      MatchOut out, PairRec* __restrict__ pairs)
@@ -1161,11 +1171,22 @@ static const SearchConfig& search_config()
 // per job), and a warp count that gives every warp the same number of items.
 static uint32_t fit_ctas_per_job(const ::b200icp* ctx, size_t max_points, size_t njobs)
 {
+    // CTAs of the fit kernel resident on one SM (registers): one full wave for
+    // a single job, never a ragged second one
+    static int resident = 0;
+    if (resident == 0)
+    {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fit_plane_kernel<6, false>, kChunk, 0) !=
+                cudaSuccess || occ < 1)
+            occ = 3;
+        resident = occ;
+    }
     const size_t items = std::max<size_t>(1, (max_points + kItem - 1) / kItem);
     const size_t warps_per_cta = kChunk / 32;
-    size_t       max_warps = (size_t)ctx->sm_count * 16;  // 4 CTAs of 4 warps per SM
-    max_warps = std::max<size_t>(warps_per_cta * 2, (2 * max_warps + njobs - 1) / njobs);
-    max_warps = std::min<size_t>(max_warps, (size_t)ctx->sm_count * 16);
+    const size_t wave_warps = (size_t)ctx->sm_count * resident * warps_per_cta;
+    size_t       max_warps = std::max<size_t>(warps_per_cta * 2, (2 * wave_warps + njobs - 1) / njobs);
+    max_warps = std::min<size_t>(max_warps, wave_warps);
     const size_t per_warp = (items + max_warps - 1) / max_warps;
     const size_t warps = (items + per_warp - 1) / per_warp;
     return (uint32_t)std::max<size_t>(1, (warps + warps_per_cta - 1) / warps_per_cta);
@@ -1374,12 +1395,21 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
 
     const dim3     mgrid(G, (unsigned)n);
     const MatchOut no_out = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    // Iterations are enqueued in batches and the host looks at the active-job
+    // counter one batch behind, so the stream never drains; launches enqueued
+    // after the last job has finished exit at once but still cost ~2.5 us each.
+    // A single registration (the odometry call) therefore sizes its first batch
+    // from the previous call on this ICP object -- consecutive scans need about
+    // the same number of iterations -- and checks it right away.
     const uint32_t kBatch = 4;
+    const bool     predict = (n == 1) && ctx->expected_runs.load() > 0;
+    const uint32_t first = predict ? (uint32_t)std::min(std::max(ctx->expected_runs.load() + 1, 2), 24) : kBatch;
     uint32_t       enq = 0, batch = 0;
     bool           finished = false;
     while (enq < D.max_iterations && !finished)
     {
-        const uint32_t todo = std::min(kBatch, D.max_iterations - enq);
+        const uint32_t want = (batch == 0) ? first : (predict ? 2u : kBatch);
+        const uint32_t todo = std::min(want, D.max_iterations - enq);
         for (uint32_t i = 0; i < todo; i++, enq++)
         {
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 0], s));
@@ -1414,6 +1444,11 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
             B2_CUDA_TRY(cudaEventSynchronize(ws->ev[slot ^ 1]));
             if (h_flags[slot ^ 1] == 0) finished = true;
         }
+        else if (predict)
+        {  // most likely the whole registration: look at it now
+            B2_CUDA_TRY(cudaEventSynchronize(ws->ev[slot]));
+            if (h_flags[slot] == 0) finished = true;
+        }
         batch++;
     }
     // QualityEvaluator_PairedRatio: one more search (k = 1, its own radius) on every job
@@ -1444,6 +1479,7 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
                                        D.max_iterations);
         max_runs = std::max(max_runs, runs);
     }
+    if (n == 1) ctx->expected_runs.store((int)max_runs);
     if (prof)
     {
         double mm = 0, fm = 0, sm = 0;
@@ -1573,9 +1609,17 @@ int run_knn(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, co
     const size_t   dbg_items = (nq + kItem - 1) / kItem + 1;
     if (getenv("B200ICP_DBG_ITEMS"))
     {
-        B2_CUDA_TRY(cudaMalloc(&d_dbg, dbg_items * sizeof(uint32_t)));
-        B2_CUDA_TRY(cudaMemset(d_dbg, 0, dbg_items * sizeof(uint32_t)));
+        B2_CUDA_TRY(cudaMalloc(&d_dbg, 3 * dbg_items * sizeof(uint32_t)));
+        B2_CUDA_TRY(cudaMemset(d_dbg, 0, 3 * dbg_items * sizeof(uint32_t)));
         B2_CUDA_TRY(cudaMemcpyToSymbol(g_dbg_item_cycles, &d_dbg, sizeof(d_dbg)));
+#ifdef B200ICP_DBG_COUNT
+        {
+            uint32_t* d_cnt = nullptr;
+            B2_CUDA_TRY(cudaMalloc(&d_cnt, (size_t)1 << 22));
+            B2_CUDA_TRY(cudaMemset(d_cnt, 0, (size_t)1 << 22));
+            B2_CUDA_TRY(cudaMemcpyToSymbol(g_dbg_lane_cand, &d_cnt, sizeof(d_cnt)));
+        }
+#endif
     }
     if (k == 1)
         launch_search_k<1>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
@@ -1589,8 +1633,28 @@ int run_knn(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, co
     B2_CUDA_TRY(cudaGetLastError());
     if (d_dbg)
     {
-        std::vector<uint32_t> h(dbg_items);
-        B2_CUDA_TRY(cudaMemcpy(h.data(), d_dbg, dbg_items * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> h(3 * dbg_items);
+        B2_CUDA_TRY(cudaMemcpy(h.data(), d_dbg, 3 * dbg_items * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+#ifdef B200ICP_DBG_COUNT
+        {   // the 25 slowest items: cycles, candidates of the busiest lane, mean candidates per lane
+            const size_t ni = (nq + kItem - 1) / kItem;
+            std::vector<size_t> ord(ni);
+            for (size_t i = 0; i < ni; i++) ord[i] = i;
+            std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return (h[a] & 0x7FFFFFFFu) > (h[b] & 0x7FFFFFFFu); });
+            double tot = 0, totmax = 0;
+            for (size_t i = 0; i < ni; i++) tot += h[ni + 2 + 2 * i], totmax += 32.0 * h[ni + 1 + 2 * i];
+            fprintf(stderr, "[dbg items] candidates: sum over lanes %.3g, 32 x max lane %.3g (lane efficiency %.2f)\n", tot, totmax, tot / totmax);
+            for (size_t r = 0; r < 25 && r < ni; r++)
+            {
+                const size_t i = ord[r];
+                fprintf(stderr, "[dbg items] #%zu item %zu cycles %u %s max-lane %u mean-lane %.0f\n", r, i, h[i] & 0x7FFFFFFFu,
+                        (h[i] & 0x80000000u) ? "fallback" : "tiled", h[ni + 1 + 2 * i], h[ni + 2 + 2 * i] / 32.0);
+            }
+            h.resize(ni);
+        }
+#else
+        h.resize(dbg_items);
+#endif
         uint32_t* null_ptr = nullptr;
         B2_CUDA_TRY(cudaMemcpyToSymbol(g_dbg_item_cycles, &null_ptr, sizeof(null_ptr)));
         cudaFree(d_dbg);

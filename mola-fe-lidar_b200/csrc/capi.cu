@@ -1,7 +1,11 @@
 // capi.cu -- extern "C" entry points declared in include/b200icp.h.
 #include <cmath>
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <vector>
 
 #include "runtime.cuh"
 
@@ -49,6 +53,27 @@ extern "C" int b200icp_create(const b200icp_params_t* params, int device, b200ic
     B2_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thr = UINT64_MAX;
     B2_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    {
+        // Give the pool a reserve once per device: growing it later (keyframe
+        // clouds stay alive in the world model, LidarOdometry.cpp:384-388) maps
+        // fresh memory inside cudaMallocAsync, a multi-millisecond stall on the
+        // per-scan path.  1 GiB of 180; returned to the pool at once.
+        static std::mutex       pm;
+        static std::vector<int> primed;
+        std::lock_guard<std::mutex> lk(pm);
+        if (std::find(primed.begin(), primed.end(), device) == primed.end())
+        {
+            void* p = nullptr;
+            if (cudaMallocAsync(&p, (size_t)1 << 30, 0) == cudaSuccess)
+            {
+                cudaFreeAsync(p, 0);
+                cudaStreamSynchronize(0);
+            }
+            else
+                cudaGetLastError();  // a small or busy device: not an error
+            primed.push_back(device);
+        }
+    }
     auto* ctx = new (std::nothrow) b200icp();
     if (!ctx) return B200ICP_ERR_NOMEM;
     ctx->device = device;

@@ -22,6 +22,10 @@
 
 namespace b2
 {
+#ifdef B200ICP_DBG_COUNT
+// development probe: candidates scanned per thread since the last reset
+static __device__ uint32_t* g_dbg_lane_cand = nullptr;
+#endif
 __device__ __forceinline__ uint64_t make_key(float d2, uint32_t idx)
 {
     return ((uint64_t)__float_as_uint(d2) << 32) | (uint64_t)idx;
@@ -113,6 +117,9 @@ __device__ __forceinline__ void scan_range(const float4* __restrict__ pts, uint3
                                            uint32_t end, float qx, float qy, float qz,
                                            uint64_t (&key)[K])
 {
+#ifdef B200ICP_DBG_COUNT
+    if (g_dbg_lane_cand) g_dbg_lane_cand[(blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x] += end - beg;
+#endif
     uint32_t j = beg;
 #if B200ICP_SCAN8
     for (; j + 8 <= end; j += 8)

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <mutex>
@@ -80,6 +81,7 @@ struct b200icp
     bool                               profile_on = false;
     b200icp_profile_t                  prof;
     int                                sm_count = 148;
+    std::atomic<int>                   expected_runs{0};  // matcher runs of the last single registration
     // index-build timings are resolved lazily (profile_get / reset) so that
     // profiling adds no host synchronisation to the upload path
     struct PendingIndexTime

@@ -216,8 +216,11 @@ DeviceCloud::Ptr LidarOdometry::make_cloud(const CObservation& o)
 {
     b200icp_t*       ctx = params_.icp.at(AlignKind::LidarOdometry).icp;
     b200icp_cloud_t* raw = nullptr;
-    check_rc(b200icp_cloud_upload(ctx, o.xs(), o.ys(), o.zs(), o.size(), cloud_search_radius_, &raw),
-             "b200icp_cloud_upload");
+    {   // observation -> device cloud + search index (apply_generators, cpp:215-217)
+        ProfilerEntry tle0(profiler_, "doProcessNewObservation.0.upload_and_index");
+        check_rc(b200icp_cloud_upload(ctx, o.xs(), o.ys(), o.zs(), o.size(), cloud_search_radius_, &raw),
+                 "b200icp_cloud_upload");
+    }
     auto              raw_ptr = std::make_shared<DeviceCloud>(raw);
     ProfilerEntry     tle1(profiler_, "doProcessNewObservation.1.filter_pointclouds");
     if (params_.voxel_decimation_resolution > 0)

@@ -244,7 +244,8 @@ extern "C" size_t b200lo_dump_profile(b200lo_t* lo, char* buf, size_t cap)
     if (!lo) return 0;
     std::ostringstream o;
     o.precision(9);
-    for (const auto& kv : lo->lo->profiler_.stats()) o << kv.first << "," << kv.second.n << "," << kv.second.total << "\n";
+    for (const auto& kv : lo->lo->profiler_.stats())
+        o << kv.first << "," << kv.second.n << "," << kv.second.total << "," << kv.second.max << "\n";
     return copy_out(o.str(), buf, cap);
 }
 

@@ -162,8 +162,8 @@ class LidarOdometry:
     def profile(self):
         out = {}
         for line in self._dump(lib().b200lo_dump_profile).splitlines():
-            name, cnt, tot = line.rsplit(",", 2)
-            out[name] = (int(cnt), float(tot))
+            name, cnt, tot, mx = line.rsplit(",", 3)
+            out[name] = (int(cnt), float(tot), float(mx))
         return out
 
     def icp_handle(self, kind=0):

@@ -12,11 +12,10 @@ box, one process per GPU over torch.distributed:
    their shard, and the per-rank partial arg-min lists are merged over NVLink.
    A partial result is a packed key (d2 as float32 bits) << 32 | global index:
    its integer order IS the (d2, index) order of the tie rule (Appendix A.4),
-   so k = 1 merges with ONE all-reduce(MIN) on int64 and k > 1 with an
-   all-to-all of the per-query lists, a k-way merge kernel
-   (b200icp_merge_keys_device) on the owner of each query slice and an
-   all-gather of the merged slices.  Results equal the unsharded search bit
-   for bit.
+   so k = 1 merges with ONE all-reduce(MIN) on int64 and k > 1 with one
+   all-gather of the per-query lists followed by the k-way merge kernel
+   (b200icp_merge_keys_device).  Results equal the unsharded search bit for
+   bit.
 
 The search / merge kernels are injected (`ShardSearch`): CudaShardSearch is the
 product path (C ABI, device tensors, NCCL); tests on CPU ranks (gloo) inject a
@@ -174,14 +173,15 @@ class ShardedMap:
             dist.all_reduce(keys, op=dist.ReduceOp.MIN)
             self.last_exchange_bytes = keys.numel() * 8
             return keys
+        # every rank gathers every rank's per-query lists (one all-gather over
+        # NVLink) and merges them with the k-way merge kernel
         nq = keys.shape[0]
-        per = (nq + self.world - 1) // self.world
-        send = torch.full((self.world * per, k), NO_KEY, dtype=torch.int64, device=keys.device)
-        send[:nq] = keys
-        recv = torch.empty_like(send)
-        dist.all_to_all_single(recv, send)  # rank r receives every rank's lists of ITS query slice
-        merged = self.search.merge(recv.view(self.world, per, k))
-        parts = [torch.empty_like(merged) for _ in range(self.world)]
-        dist.all_gather(parts, merged)
-        self.last_exchange_bytes = send.numel() * 8 + merged.numel() * 8 * self.world
-        return torch.cat(parts, dim=0)[:nq]
+        parts = torch.empty((self.world, nq, k), dtype=torch.int64, device=keys.device)
+        if hasattr(dist, "all_gather_into_tensor") and keys.is_cuda:
+            dist.all_gather_into_tensor(parts, keys)
+        else:  # gloo (CPU test ranks)
+            lst = [torch.empty_like(keys) for _ in range(self.world)]
+            dist.all_gather(lst, keys)
+            parts = torch.stack(lst)
+        self.last_exchange_bytes = parts.numel() * 8
+        return self.search.merge(parts)

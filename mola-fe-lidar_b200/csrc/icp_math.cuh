@@ -409,9 +409,17 @@ B2_HD int inverse6(const double* A, double* Ainv);
 // in registers (the pivoted QR above indexes dynamically and goes through
 // local memory). Returns false when a pivot is not safely positive: the
 // caller then falls back to the rank-revealing QR.
-B2_HD bool chol_solve6(const double* H, const double* b, double* x)
+// Factor: L (lower, unit-free) with the reciprocals of its diagonal, so that the
+// two triangular solves multiply instead of dividing (FP64 division and square
+// root are long dependent instruction sequences on the device).
+struct Chol6
 {
     double L[6][6];
+    double inv[6];
+};
+
+B2_HD bool chol_factor6(const double* H, Chol6& F)
+{
     double dmax = 0;
 #pragma unroll
     for (int i = 0; i < 6; i++) dmax = fmax(dmax, H[i * 6 + i]);
@@ -421,37 +429,50 @@ B2_HD bool chol_solve6(const double* H, const double* b, double* x)
     {
         double s = H[j * 6 + j];
 #pragma unroll
-        for (int k = 0; k < j; k++) s -= L[j][k] * L[j][k];
+        for (int k = 0; k < j; k++) s -= F.L[j][k] * F.L[j][k];
         if (!(s > tiny)) return false;
         const double d = sqrt(s);
         const double inv = 1.0 / d;
-        L[j][j] = d;
+        F.L[j][j] = d;
+        F.inv[j] = inv;
 #pragma unroll
         for (int i = j + 1; i < 6; i++)
         {
             double t = H[i * 6 + j];
 #pragma unroll
-            for (int k = 0; k < j; k++) t -= L[i][k] * L[j][k];
-            L[i][j] = t * inv;
+            for (int k = 0; k < j; k++) t -= F.L[i][k] * F.L[j][k];
+            F.L[i][j] = t * inv;
         }
     }
+    return true;
+}
+
+B2_HD void chol_apply6(const Chol6& F, const double* b, double* x)
+{
     double y[6];
 #pragma unroll
     for (int i = 0; i < 6; i++)
     {
         double s = b[i];
 #pragma unroll
-        for (int k = 0; k < i; k++) s -= L[i][k] * y[k];
-        y[i] = s / L[i][i];
+        for (int k = 0; k < i; k++) s -= F.L[i][k] * y[k];
+        y[i] = s * F.inv[i];
     }
 #pragma unroll
     for (int i = 5; i >= 0; i--)
     {
         double s = y[i];
 #pragma unroll
-        for (int k = i + 1; k < 6; k++) s -= L[k][i] * x[k];
-        x[i] = s / L[i][i];
+        for (int k = i + 1; k < 6; k++) s -= F.L[k][i] * x[k];
+        x[i] = s * F.inv[i];
     }
+}
+
+B2_HD bool chol_solve6(const double* H, const double* b, double* x)
+{
+    Chol6 F;
+    if (!chol_factor6(H, F)) return false;
+    chol_apply6(F, b, x);
     return true;
 }
 
@@ -465,17 +486,17 @@ B2_HD void solve6_spd(const double* H, const double* b, double* x)
 // inverse of a symmetric 6x6: Cholesky column by column, QR on failure
 B2_HD int inverse6_spd(const double* A, double* Ainv)
 {
-    bool ok = true;
+    Chol6 F;
+    if (!chol_factor6(A, F)) return inverse6(A, Ainv);
 #pragma unroll 1
-    for (int c = 0; c < 6 && ok; c++)
+    for (int c = 0; c < 6; c++)
     {
         double e[6] = {0, 0, 0, 0, 0, 0}, x[6];
         e[c] = 1.0;
-        ok = chol_solve6(A, e, x);
+        chol_apply6(F, e, x);
         for (int i = 0; i < 6; i++) Ainv[i * 6 + c] = x[i];
     }
-    if (ok) return 6;
-    return inverse6(A, Ainv);
+    return 6;
 }
 
 B2_HD int inverse6(const double* A, double* Ainv)

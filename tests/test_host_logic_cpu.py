@@ -153,3 +153,30 @@ def test_async_queue_and_extra_edges_use_batch_api(fake_lib):
     assert r["n_checked_pairs"] >= 1, r
     assert r["n_factors"] >= r["n_keyframes"] - 1
     assert "onNewObservation" in r["profile"] and "delay_onNewObs_to_process" in r["profile"]
+
+
+def test_additive_key_disables_extra_edge_checks(fake_lib):
+    """b200_extra_edge_checks: false (additive key, used by bench.py's e2e leg)
+    skips checkForNearbyKFs (cpp:493-508): key-frames and odometry factors are
+    unchanged, no pair is ever sent to the second pool."""
+    body = """
+        lo = lom.LidarOdometry(yaml_text=lom.system_yaml(extra=%r))
+        k = 0
+        for i in range(21):
+            lo.onNewObservation(scan(2.0 * i), 0.1 * k, sync=True); k += 1
+        for i in range(20, -1, -1):
+            lo.onNewObservation(scan(2.0 * i, y=6.0), 0.1 * k, sync=True); k += 1
+        lo.wait_idle()
+        s = lo.state()
+        out["n_keyframes"] = int(s["n_keyframes"]); out["n_checked_pairs"] = int(s["n_checked_pairs"])
+        out["n_icp"] = int(s["n_icp"]); out["n_processed"] = int(s["n_processed"])
+        out["profile"] = sorted(lo.profile().keys())
+        lo.close()
+    """
+    on = run_child(fake_lib, body % "")
+    off = run_child(fake_lib, body % "  b200_extra_edge_checks: false\n")
+    assert on["n_keyframes"] == off["n_keyframes"] >= 10
+    assert on["n_checked_pairs"] >= 1 and off["n_checked_pairs"] == 0
+    assert off["n_icp"] == off["n_processed"] - 1  # exactly one registration per scan after the first
+    assert "doProcessNewObservation.6.checkForNearbyKFs" not in off["profile"]
+    assert "doProcessNewObservation.0.upload_and_index" in off["profile"]

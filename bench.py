@@ -314,8 +314,15 @@ def sharded_knn(torch, dist, capi, scans, poses, rank, world, local_rank, dev, m
     wp = np.concatenate(world_points(scans, poses))
     rng = np.random.default_rng(5)  # same map on every rank
     total = map_per_gpu * world
-    reps = (total + len(wp) - 1) // len(wp)
-    themap = np.concatenate([wp + rng.normal(0, 0.03, size=wp.shape).astype(np.float32) for _ in range(reps)])[:total]
+    # the mapped stretch = the scans in one frame, cropped to 60 m around the vehicle, jittered copies up to
+    # map_per_gpu points.  It is repeated `world` times on a 130 m lattice: the map grows with the GPUs at
+    # constant density, as a larger mapped area does, and stays inside the 700 m the 0.7 m block grid spans
+    ctr = wp.mean(axis=0)
+    near = wp[(np.abs(wp[:, 0] - ctr[0]) < 60.0) & (np.abs(wp[:, 1] - ctr[1]) < 60.0)]
+    reps = (map_per_gpu + len(near) - 1) // len(near)
+    stretch = np.concatenate([near + rng.normal(0, 0.03, size=near.shape).astype(np.float32)
+                              for _ in range(reps)])[:map_per_gpu]
+    themap = np.concatenate([stretch + np.float32([130.0 * (j % 3), 130.0 * (j // 3), 0.0]) for j in range(world)])
     owner = M.partition_by_cell(themap, world, cell=4.0, mode="interleaved")
     mine = M.shard_indices(owner, rank)
     # one 128-beam scan (260,096 points) taken in the middle of the mapped stretch
@@ -328,26 +335,52 @@ def sharded_knn(torch, dist, capi, scans, poses, rank, world, local_rank, dev, m
     qc = search.upload_queries(queries, 0.7)
     out = {"workload": "c5_sharded_map_knn", "n_queries": len(queries), "map_points": int(total),
            "map_points_this_rank": int(len(mine)), "partition": "4 m (x,y) cells interleaved over the ranks",
-           "scaling": "weak", "cases": []}
+           "scaling": "map size grows with N at constant density (the mapped stretch repeated on a 130 m lattice); "
+                      "the one scan overlaps one stretch, so each rank searches 1/N of its neighbourhood",
+           "timing": "best of 4 single queries, max over ranks each", "cases": []}
     for k in (1, 6):
         sm.query(qc, k, 0.7)
         if dist is not None:
             dist.barrier()
         icp.profile_enable(True)
         icp.profile_reset()
-        ms, keys = timed(torch, lambda: [sm.query(qc, k, 0.7) for _ in range(3)][-1])
-        ms /= 3
+        ms = 1e30
+        for _ in range(4):  # best of 4: single calls of a few hundred microseconds are sensitive to host hiccups
+            m1, keys = timed(torch, lambda: sm.query(qc, k, 0.7))
+            if dist is not None:
+                tt = torch.tensor([m1], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                m1 = float(tt[0])
+            ms = min(ms, m1)
         pr = icp.profile()
         icp.profile_enable(False)
         search_ms = pr["knn_ms"] / max(pr["knn_launches"], 1)
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
         found = int((keys != M.NO_KEY).sum().item())
-        out["cases"].append({"k": k, "radius_m": 0.7, "ms": float(t[0]), "queries_per_s": len(queries) / (float(t[0]) * 1e-3),
-                             "neighbours_found": found, "exchange_bytes_per_rank": int(sm.last_exchange_bytes),
-                             "merge": "all_reduce(MIN, int64)" if k == 1 else "all_gather + k-way merge kernel",
-                             "search_kernel_ms_rank0": search_ms})
+        case = {"k": k, "radius_m": 0.7, "ms": ms, "queries_per_s": len(queries) / (ms * 1e-3),
+                "neighbours_found": found, "exchange_bytes_per_rank": int(sm.last_exchange_bytes),
+                "merge": "all_reduce(MIN, int64)" if k == 1 else "all_gather + k-way merge kernel",
+                "search_kernel_ms_rank0": search_ms}
+        # the fused variant: the search kernel stores into every rank's buffer over NVLink (peer memory),
+        # only barriers go through NCCL
+        try:
+            fk = sm.query_fused(qc, k, 0.7)
+            same = bool(torch.equal(fk, keys))
+            fms = 1e30
+            for _ in range(4):
+                m1, fk = timed(torch, lambda: sm.query_fused(qc, k, 0.7))
+                if dist is not None:
+                    tt = torch.tensor([m1], device=dev, dtype=torch.float64)
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    m1 = float(tt[0])
+                fms = min(fms, m1)
+            case["fused_peer_memory"] = {"ms": fms, "queries_per_s": len(queries) / (fms * 1e-3),
+                                         "identical_to_nccl_path": same,
+                                         "how": "search + atomicMin_system into every rank's slot" if k == 1
+                                         else "search + P2P row stores into every rank's buffer, then the merge kernel"}
+        except Exception as e:
+            case["fused_peer_memory"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        out["cases"].append(case)
+    sm.close()
     qc.free()
     search.close()
     icp.close()

@@ -186,6 +186,50 @@ int b200icp_knn_keys_device(b200icp_t* icp, const b200icp_cloud_t* ref, const b2
 int b200icp_merge_keys_device(b200icp_t* icp, const uint64_t* d_parts, uint32_t parts,
                               size_t part_stride, size_t nq, uint32_t k, uint64_t* d_out);
 
+/* Fused search + exchange over peer memory (NVLink): the search kernel itself
+ * stores every result row into the gather buffer of EVERY rank at
+ * [rank][query][k] (P2P stores, overlapping the search), or -- k = 1 with
+ * `atomic_min` -- folds its key into every rank's [query] slot with a
+ * system-scope atomicMin, so that after a barrier each rank holds the merged
+ * arg-min without any collective data movement.  d_gather[r] is rank r's
+ * buffer as mapped into THIS process (own buffer: the local pointer; peers:
+ * b200icp_peer_open).  Buffers must hold world*nq*k keys (nq keys with
+ * atomic_min, pre-filled with B200ICP_NO_KEY by their owner).  The caller
+ * orders the phases across ranks (barrier before: buffers ready; barrier
+ * after: all stores have landed). */
+int b200icp_knn_keys_scatter(b200icp_t* icp, const b200icp_cloud_t* ref, const b200icp_cloud_t* queries,
+                             const double* pose6, uint32_t k, float max_dist,
+                             const uint32_t* d_index_map, uint64_t* const* d_gather, uint32_t world,
+                             uint32_t rank, int atomic_min);
+/* Exchange buffers: zero-initialised device memory that other processes on the
+ * same node can map (CUDA IPC).  handle_out: 64 opaque bytes to hand to the peers. */
+int b200icp_peer_alloc(b200icp_t* icp, size_t bytes, void** d_ptr, unsigned char handle_out[64]);
+int b200icp_peer_free(b200icp_t* icp, void* d_ptr);
+int b200icp_peer_open(b200icp_t* icp, const unsigned char handle[64], void** d_peer_ptr);
+int b200icp_peer_close(b200icp_t* icp, void* d_peer_ptr);
+/* Barrier across the ranks of one node through peer memory, no collective
+ * library: d_flags[r] = rank r's flag array (>= 8 uint64, zero-initialised, in
+ * an exchange buffer), `epoch` a number that grows by one per barrier.  A tiny
+ * kernel stores `epoch` into slot [rank] of every rank's array (system-scope
+ * release, after everything this handle's stream has written) and waits until
+ * its own array shows `epoch` in all slots.  Returns B200ICP_ERR_CUDA if a peer
+ * did not arrive within ~2 s (never spins forever). */
+int b200icp_peer_barrier(b200icp_t* icp, uint64_t* const* d_flags, uint32_t world, uint32_t rank,
+                         uint64_t epoch);
+/* The whole sharded query in ONE call on one stream with one host
+ * synchronisation: reset, barrier, search with scatter into every rank's buffer
+ * (atomicMin for k = 1), barrier, merge into d_out[nq*k] (device).  d_bases[r]:
+ * rank r's exchange buffer as mapped here (b200icp_peer_alloc / _open), at least
+ * 256 + world*nq*k*8 bytes: barrier flags in the first 256 bytes, keys after
+ * them.  *epoch_io: the barrier epoch, same start value (0) on every rank,
+ * advanced by the call. */
+int b200icp_knn_keys_exchange(b200icp_t* icp, const b200icp_cloud_t* ref, const b200icp_cloud_t* queries,
+                              const double* pose6, uint32_t k, float max_dist,
+                              const uint32_t* d_index_map, uint64_t* const* d_bases, uint32_t world,
+                              uint32_t rank, uint64_t* epoch_io, uint64_t* d_out);
+/* fills n keys at a device pointer with B200ICP_NO_KEY (exchange-buffer reset) */
+int b200icp_fill_no_key(b200icp_t* icp, uint64_t* d_keys, size_t n);
+
 /* --- matcher at a fixed pose (Matcher_Point2Plane; parity hook) ---------- */
 /* Host outputs in the local cloud's ORIGINAL order: paired[n] (0/1),
  * nn_idx[n*knn] (after the distance cut, padded INVALID), nn_cnt[n],

@@ -92,6 +92,8 @@ EXPORTS = [
     "b200icp_get_params", "b200icp_device", "b200icp_cloud_upload", "b200icp_cloud_from_device",
     "b200icp_cloud_free", "b200icp_cloud_size", "b200icp_cloud_download",
     "b200icp_voxel_decimate", "b200icp_knn", "b200icp_knn_keys_device", "b200icp_merge_keys_device",
+    "b200icp_knn_keys_scatter", "b200icp_peer_alloc", "b200icp_peer_free", "b200icp_peer_open",
+    "b200icp_peer_close", "b200icp_peer_barrier", "b200icp_knn_keys_exchange", "b200icp_fill_no_key",
     "b200icp_match", "b200icp_align",
     "b200icp_align_batch", "b200icp_profile_enable", "b200icp_profile_reset",
     "b200icp_profile_get", "b200icp_synchronize",
@@ -132,6 +134,16 @@ def lib():
     L.b200icp_knn.argtypes = [vp, vp, vp, dp, C.c_uint32, C.c_float, up, fp]
     L.b200icp_knn_keys_device.argtypes = [vp, vp, vp, dp, C.c_uint32, C.c_float, vp, vp]
     L.b200icp_merge_keys_device.argtypes = [vp, vp, C.c_uint32, C.c_size_t, C.c_size_t, C.c_uint32, vp]
+    L.b200icp_knn_keys_scatter.argtypes = [vp, vp, vp, dp, C.c_uint32, C.c_float, vp, C.POINTER(vp),
+                                           C.c_uint32, C.c_uint32, C.c_int]
+    L.b200icp_peer_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.c_char_p]
+    L.b200icp_peer_free.argtypes = [vp, vp]
+    L.b200icp_peer_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    L.b200icp_peer_close.argtypes = [vp, vp]
+    L.b200icp_peer_barrier.argtypes = [vp, C.POINTER(vp), C.c_uint32, C.c_uint32, C.c_uint64]
+    L.b200icp_knn_keys_exchange.argtypes = [vp, vp, vp, dp, C.c_uint32, C.c_float, vp, C.POINTER(vp),
+                                            C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), vp]
+    L.b200icp_fill_no_key.argtypes = [vp, vp, C.c_size_t]
     L.b200icp_match.argtypes = [vp, vp, vp, dp, C.POINTER(C.c_uint8), up, up, dp, dp, up]
     L.b200icp_align.argtypes = [vp, vp, vp, dp, C.POINTER(Result)]
     L.b200icp_align_batch.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(vp), dp,
@@ -282,6 +294,57 @@ class ICP:
         _check(lib().b200icp_knn_keys_device(self.h, ref.h, queries.h,
                                              None if pose is None else _ptr(pose, C.c_double), k, max_dist,
                                              d_index_map or None, d_keys_out))
+
+    def knn_keys_scatter(self, ref, queries, k, max_dist, gather_ptrs, rank, d_index_map=0, atomic_min=False,
+                         pose6=None):
+        """Fused search + exchange: rows (or, k = 1 with atomic_min, the folded
+        minimum) stored straight into every rank's gather buffer over NVLink.
+        gather_ptrs: device pointers of the ranks' buffers as mapped here."""
+        pose = None if pose6 is None else np.ascontiguousarray(pose6, dtype=np.float64)
+        arr = (C.c_void_p * len(gather_ptrs))(*gather_ptrs)
+        _check(lib().b200icp_knn_keys_scatter(self.h, ref.h, queries.h,
+                                              None if pose is None else _ptr(pose, C.c_double), k, max_dist,
+                                              d_index_map or None, arr, len(gather_ptrs), rank,
+                                              int(bool(atomic_min))))
+
+    def peer_alloc(self, nbytes):
+        """(device pointer, 64-byte IPC handle) of an exchange buffer other ranks can map."""
+        p = C.c_void_p()
+        h = C.create_string_buffer(64)
+        _check(lib().b200icp_peer_alloc(self.h, nbytes, C.byref(p), h))
+        return p.value, h.raw
+
+    def peer_open(self, handle):
+        p = C.c_void_p()
+        _check(lib().b200icp_peer_open(self.h, handle, C.byref(p)))
+        return p.value
+
+    def peer_close(self, ptr):
+        _check(lib().b200icp_peer_close(self.h, ptr))
+
+    def peer_free(self, ptr):
+        _check(lib().b200icp_peer_free(self.h, ptr))
+
+    def peer_barrier(self, flag_ptrs, rank, epoch):
+        """Barrier of the node's ranks through peer memory (no collective library)."""
+        arr = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)
+        _check(lib().b200icp_peer_barrier(self.h, arr, len(flag_ptrs), rank, epoch))
+
+    def knn_keys_exchange(self, ref, queries, k, max_dist, base_ptrs, rank, epoch, d_out, d_index_map=0,
+                          pose6=None):
+        """The whole sharded query in one call (see b200icp_knn_keys_exchange);
+        returns the advanced barrier epoch."""
+        pose = None if pose6 is None else np.ascontiguousarray(pose6, dtype=np.float64)
+        arr = (C.c_void_p * len(base_ptrs))(*base_ptrs)
+        ep = C.c_uint64(epoch)
+        _check(lib().b200icp_knn_keys_exchange(self.h, ref.h, queries.h,
+                                               None if pose is None else _ptr(pose, C.c_double), k, max_dist,
+                                               d_index_map or None, arr, len(base_ptrs), rank, C.byref(ep),
+                                               d_out))
+        return ep.value
+
+    def fill_no_key(self, d_keys, n):
+        _check(lib().b200icp_fill_no_key(self.h, d_keys, n))
 
     def merge_keys_device(self, d_parts, parts, part_stride, nq, k, d_out):
         """k smallest of `parts` ascending key lists per query, device pointers."""

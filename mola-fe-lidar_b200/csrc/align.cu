@@ -162,6 +162,44 @@ struct KeyWriter
     }
 };
 
+// The same keys stored into the gather buffers of all ranks of a sharded map
+// (SURVEY 8e): peer[r] is rank r's buffer mapped over NVLink.  Rows go to
+// [rank][query][k] of every buffer (search + all-gather in one kernel); with
+// `amin` (k = 1) the key is folded into slot [query] of every buffer with a
+// system-scope atomicMin (search + all-reduce(MIN) in one kernel).
+struct KeyScatter
+{
+    uint64_t*       peer[8];
+    const uint32_t* map;
+    uint32_t        k, world, rank, nq, amin;
+    template <int K>
+    __device__ __forceinline__ void operator()(JobDev&, bool has, uint32_t, uint32_t orig,
+                                               const uint64_t (&key)[K], uint64_t sent) const
+    {
+        if (!has) return;
+#pragma unroll
+        for (int i = 0; i < K; i++)
+            if ((uint32_t)i < k)
+            {
+                uint64_t v = B200ICP_NO_KEY;
+                if (key[i] != sent)
+                {
+                    const uint32_t li = key_idx(key[i]);
+                    v = (key[i] & 0xFFFFFFFF00000000ull) | (uint64_t)(map ? __ldg(map + li) : li);
+                }
+                if (amin)
+                {
+                    if (v != B200ICP_NO_KEY)
+                        for (uint32_t r = 0; r < world; r++)
+                            atomicMin_system(reinterpret_cast<unsigned long long*>(peer[r]) + orig,
+                                             (unsigned long long)v);
+                }
+                else
+                    for (uint32_t r = 0; r < world; r++) peer[r][((size_t)rank * nq + orig) * k + i] = v;
+            }
+    }
+};
+
 // QualityEvaluator_PairedRatio (row O / A.8): queries with a neighbour at d2 < thr2 (strict)
 struct HitCounter
 {
@@ -1736,6 +1774,217 @@ int run_knn_keys(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* 
         ctx->prof.knn_ms += ms;
         ctx->prof.knn_queries += nq;
     }
+    return B200ICP_OK;
+}
+
+// enqueues the scatter search on ws->stream (no host synchronisation)
+static int enqueue_scatter(::b200icp* ctx, Workspace* ws, const b200icp_cloud* ref, const b200icp_cloud* q,
+                           const double* pose6, uint32_t k, float max_dist, const uint32_t* d_index_map,
+                           uint64_t* const* d_gather, uint32_t world, uint32_t rank, int atomic_min, bool time_it)
+{
+    if (k < 1 || k > B200ICP_MAX_KNN || !(max_dist > 0) || !std::isfinite(max_dist) || (atomic_min && k != 1))
+    {
+        set_error("k=%u outside [1,%d], max_dist not positive and finite, or atomic_min with k != 1", k,
+                  B200ICP_MAX_KNN);
+        return B200ICP_ERR_BAD_ARG;
+    }
+    cudaStream_t s = ws->stream;
+    const size_t nq = q->n;
+    SingleJob    sj;
+    if (int r = single_job_setup(ws, ref, q, pose6, 0, sj, [&](Carver&) {})) return r;
+    const float cap_d2 = max_dist * max_dist;
+    KeyScatter  w;
+    memset(&w, 0, sizeof(w));
+    for (uint32_t r = 0; r < world; r++) w.peer[r] = d_gather[r];
+    w.map = d_index_map, w.k = k, w.world = world, w.rank = rank, w.nq = (uint32_t)nq, w.amin = atomic_min ? 1u : 0u;
+    if (!atomic_min)
+    {
+        // rows of non-finite queries are never visited by the search: this rank's
+        // slice of EVERY buffer is reset first
+        for (uint32_t r = 0; r < world; r++)
+            fill_u64_kernel<<<(int)((nq * k + 255) / 256), 256, 0, s>>>(d_gather[r] + (size_t)rank * nq * k, nq * k,
+                                                                          B200ICP_NO_KEY);
+        ws->launches += world;
+    }
+    if (time_it)
+    {
+        if (int r = ws->reserve_prof_events(1)) return r;
+        B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[0], s));
+    }
+    if (k == 1)
+        launch_search_k<1>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
+    else if (k <= 4)
+        launch_search_k<4>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
+    else if (k <= 6)
+        launch_search_k<6>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
+    else
+        launch_search_k<8>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
+    if (time_it) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[1], s));
+    B2_CUDA_TRY(cudaGetLastError());
+    return B200ICP_OK;
+}
+
+static int account_knn_time(::b200icp* ctx, Workspace* ws, size_t nq)
+{
+    float ms = 0;
+    B2_CUDA_TRY(cudaEventElapsedTime(&ms, ws->prof_ev[0], ws->prof_ev[1]));
+    std::lock_guard<std::mutex> lk(ctx->mtx);
+    ctx->prof.knn_launches++;
+    ctx->prof.knn_ms += ms;
+    ctx->prof.knn_queries += nq;
+    return B200ICP_OK;
+}
+
+int run_knn_keys_scatter(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, const double* pose6,
+                         uint32_t k, float max_dist, const uint32_t* d_index_map, uint64_t* const* d_gather,
+                         uint32_t world, uint32_t rank, int atomic_min)
+{
+    if (q->n == 0) return B200ICP_OK;
+    Lease L(ctx);
+    if (!L.ws) return B200ICP_ERR_CUDA;
+    const bool prof = ctx->profile_on;
+    if (int r = enqueue_scatter(ctx, L.ws, ref, q, pose6, k, max_dist, d_index_map, d_gather, world, rank,
+                                atomic_min, prof))
+        return r;
+    B2_CUDA_TRY(cudaStreamSynchronize(L.ws->stream));
+    if (prof) return account_knn_time(ctx, L.ws, q->n);
+    return B200ICP_OK;
+}
+
+// Barrier of the ranks of one node over peer memory (see b200icp_peer_barrier).
+struct PeerFlags
+{
+    uint64_t* p[8];
+};
+__global__ void peer_barrier_kernel(PeerFlags flags, uint32_t world, uint32_t rank, unsigned long long epoch,
+                                    uint32_t* __restrict__ timed_out)
+{
+    const uint32_t r = threadIdx.x;
+    if (r >= world) return;
+    __threadfence_system();  // everything this stream wrote before is visible system-wide first
+    volatile unsigned long long* mine = reinterpret_cast<volatile unsigned long long*>(flags.p[rank]);
+    volatile unsigned long long* theirs = reinterpret_cast<volatile unsigned long long*>(flags.p[r]);
+    theirs[rank] = epoch;
+    __threadfence_system();
+    const long long t0 = clock64();
+    while (mine[r] < epoch)
+    {
+        if (clock64() - t0 > 4000000000ll)
+        {  // ~2 s: a peer is missing; give up instead of hanging the GPU
+            *timed_out = 1u;
+            break;
+        }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
+int run_peer_barrier(::b200icp* ctx, uint64_t* const* d_flags, uint32_t world, uint32_t rank, uint64_t epoch)
+{
+    Lease L(ctx);
+    if (!L.ws) return B200ICP_ERR_CUDA;
+    Workspace*   ws = L.ws;
+    cudaStream_t s = ws->stream;
+    uint32_t* d_to = ws->d_flag;
+    uint32_t* h_to = ws->h_flag;
+    B2_CUDA_TRY(cudaMemsetAsync(d_to, 0, sizeof(uint32_t), s));
+    PeerFlags f;
+    memset(&f, 0, sizeof(f));
+    for (uint32_t r = 0; r < world; r++) f.p[r] = d_flags[r];
+    peer_barrier_kernel<<<1, 32, 0, s>>>(f, world, rank, (unsigned long long)epoch, d_to);
+    ws->launches++;
+    B2_CUDA_TRY(cudaMemcpyAsync(h_to, d_to, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    B2_CUDA_TRY(cudaStreamSynchronize(s));
+    B2_CUDA_TRY(cudaGetLastError());
+    if (*h_to)
+    {
+        set_error("peer barrier %llu timed out on rank %u: a rank of the node did not arrive",
+                  (unsigned long long)epoch, rank);
+        return B200ICP_ERR_CUDA;
+    }
+    return B200ICP_OK;
+}
+
+// One call, one stream, one host synchronisation (b200icp_knn_keys_exchange):
+// reset -> barrier -> search with scatter into every rank's buffer -> barrier ->
+// merge into d_out.  d_bases[r]: rank r's exchange buffer, flags at the base,
+// keys kPeerHeader bytes further.
+constexpr size_t kPeerHeader = 256;
+int run_knn_exchange(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, const double* pose6,
+                     uint32_t k, float max_dist, const uint32_t* d_index_map, uint64_t* const* d_bases,
+                     uint32_t world, uint32_t rank, uint64_t* epoch_io, uint64_t* d_out)
+{
+    const size_t nq = q->n;
+    if (nq == 0) return B200ICP_OK;
+    if (k < 1 || k > B200ICP_MAX_KNN)
+    {
+        set_error("k=%u outside [1,%d]", k, B200ICP_MAX_KNN);
+        return B200ICP_ERR_BAD_ARG;
+    }
+    Lease L(ctx);
+    if (!L.ws) return B200ICP_ERR_CUDA;
+    Workspace*   ws = L.ws;
+    cudaStream_t s = ws->stream;
+    uint64_t*    data[8];
+    PeerFlags    f;
+    memset(&f, 0, sizeof(f));
+    for (uint32_t r = 0; r < world; r++)
+    {
+        f.p[r] = d_bases[r];
+        data[r] = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(d_bases[r]) + kPeerHeader);
+    }
+    const bool amin = (k == 1);
+    const bool prof = ctx->profile_on;
+    const uint64_t e0 = *epoch_io + 1, e1 = *epoch_io + 2;
+    B2_CUDA_TRY(cudaMemsetAsync(ws->d_flag, 0, sizeof(uint32_t), s));
+    if (amin)
+    {  // own result slots back to "no neighbour" before anybody folds into them
+        fill_u64_kernel<<<(int)((nq + 255) / 256), 256, 0, s>>>(data[rank], nq, B200ICP_NO_KEY);
+        ws->launches++;
+    }
+    peer_barrier_kernel<<<1, 32, 0, s>>>(f, world, rank, (unsigned long long)e0, ws->d_flag);
+    ws->launches++;
+    if (int r = enqueue_scatter(ctx, ws, ref, q, pose6, k, max_dist, d_index_map, data, world, rank, amin ? 1 : 0,
+                                prof))
+        return r;
+    peer_barrier_kernel<<<1, 32, 0, s>>>(f, world, rank, (unsigned long long)e1, ws->d_flag);
+    ws->launches++;
+    {
+        const int      blocks = (int)((nq + 255) / 256);
+        const uint32_t parts = amin ? 1u : world;
+        if (k == 1)
+            merge_keys_kernel<1><<<blocks, 256, 0, s>>>(data[rank], parts, nq * k, nq, k, d_out);
+        else if (k <= 4)
+            merge_keys_kernel<4><<<blocks, 256, 0, s>>>(data[rank], parts, nq * k, nq, k, d_out);
+        else if (k <= 6)
+            merge_keys_kernel<6><<<blocks, 256, 0, s>>>(data[rank], parts, nq * k, nq, k, d_out);
+        else
+            merge_keys_kernel<8><<<blocks, 256, 0, s>>>(data[rank], parts, nq * k, nq, k, d_out);
+        ws->launches++;
+    }
+    B2_CUDA_TRY(cudaMemcpyAsync(ws->h_flag, ws->d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    B2_CUDA_TRY(cudaStreamSynchronize(s));
+    B2_CUDA_TRY(cudaGetLastError());
+    *epoch_io = e1;
+    if (*ws->h_flag)
+    {
+        set_error("peer barrier timed out on rank %u: a rank of the node did not arrive", rank);
+        return B200ICP_ERR_CUDA;
+    }
+    if (prof) return account_knn_time(ctx, ws, nq);
+    return B200ICP_OK;
+}
+
+int run_fill_no_key(::b200icp* ctx, uint64_t* d_keys, size_t n)
+{
+    if (n == 0) return B200ICP_OK;
+    Lease L(ctx);
+    if (!L.ws) return B200ICP_ERR_CUDA;
+    cudaStream_t s = L.ws->stream;
+    fill_u64_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(d_keys, n, B200ICP_NO_KEY);
+    L.ws->launches++;
+    B2_CUDA_TRY(cudaGetLastError());
+    B2_CUDA_TRY(cudaStreamSynchronize(s));
     return B200ICP_OK;
 }
 

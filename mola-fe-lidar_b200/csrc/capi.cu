@@ -264,6 +264,126 @@ extern "C" int b200icp_knn_keys_device(b200icp_t* icp, const b200icp_cloud_t* re
     return run_knn_keys(icp, ref, queries, pose6, k, max_dist, d_index_map, d_keys_out);
 }
 
+extern "C" int b200icp_knn_keys_scatter(b200icp_t* icp, const b200icp_cloud_t* ref,
+                                        const b200icp_cloud_t* queries, const double* pose6, uint32_t k,
+                                        float max_dist, const uint32_t* d_index_map,
+                                        uint64_t* const* d_gather, uint32_t world, uint32_t rank, int atomic_min)
+{
+    if (!icp || !ref || !queries || !d_gather || world == 0 || world > 8 || rank >= world)
+    {
+        set_error("null argument or world outside [1,8]");
+        return B200ICP_ERR_BAD_ARG;
+    }
+    for (uint32_t r = 0; r < world; r++)
+        if (!d_gather[r])
+        {
+            set_error("gather buffer of rank %u is null", r);
+            return B200ICP_ERR_BAD_ARG;
+        }
+    return run_knn_keys_scatter(icp, ref, queries, pose6, k, max_dist, d_index_map, d_gather, world, rank,
+                                atomic_min);
+}
+
+extern "C" int b200icp_peer_alloc(b200icp_t* icp, size_t bytes, void** d_ptr, unsigned char handle_out[64])
+{
+    if (!icp || !d_ptr || !handle_out || bytes == 0)
+    {
+        set_error("null argument");
+        return B200ICP_ERR_BAD_ARG;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    B2_CUDA_TRY(cudaSetDevice(icp->device));
+    void* p = nullptr;
+    B2_CUDA_TRY(cudaMalloc(&p, bytes));  // IPC needs a plain allocation, not the stream-ordered pool
+    B2_CUDA_TRY(cudaMemset(p, 0, bytes));  // barrier flags start at zero
+    B2_CUDA_TRY(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    cudaError_t        e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess)
+    {
+        set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+        cudaFree(p);
+        return B200ICP_ERR_CUDA;
+    }
+    memcpy(handle_out, &h, 64);
+    *d_ptr = p;
+    return B200ICP_OK;
+}
+
+extern "C" int b200icp_peer_free(b200icp_t* icp, void* d_ptr)
+{
+    if (!icp) return B200ICP_ERR_BAD_ARG;
+    B2_CUDA_TRY(cudaSetDevice(icp->device));
+    if (d_ptr) B2_CUDA_TRY(cudaFree(d_ptr));
+    return B200ICP_OK;
+}
+
+extern "C" int b200icp_peer_open(b200icp_t* icp, const unsigned char handle[64], void** d_peer_ptr)
+{
+    if (!icp || !handle || !d_peer_ptr)
+    {
+        set_error("null argument");
+        return B200ICP_ERR_BAD_ARG;
+    }
+    B2_CUDA_TRY(cudaSetDevice(icp->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void* p = nullptr;
+    B2_CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *d_peer_ptr = p;
+    return B200ICP_OK;
+}
+
+extern "C" int b200icp_peer_close(b200icp_t* icp, void* d_peer_ptr)
+{
+    if (!icp) return B200ICP_ERR_BAD_ARG;
+    B2_CUDA_TRY(cudaSetDevice(icp->device));
+    if (d_peer_ptr) B2_CUDA_TRY(cudaIpcCloseMemHandle(d_peer_ptr));
+    return B200ICP_OK;
+}
+
+extern "C" int b200icp_peer_barrier(b200icp_t* icp, uint64_t* const* d_flags, uint32_t world, uint32_t rank,
+                                    uint64_t epoch)
+{
+    if (!icp || !d_flags || world == 0 || world > 8 || rank >= world)
+    {
+        set_error("null argument or world outside [1,8]");
+        return B200ICP_ERR_BAD_ARG;
+    }
+    return run_peer_barrier(icp, d_flags, world, rank, epoch);
+}
+
+extern "C" int b200icp_knn_keys_exchange(b200icp_t* icp, const b200icp_cloud_t* ref,
+                                         const b200icp_cloud_t* queries, const double* pose6, uint32_t k,
+                                         float max_dist, const uint32_t* d_index_map,
+                                         uint64_t* const* d_bases, uint32_t world, uint32_t rank,
+                                         uint64_t* epoch_io, uint64_t* d_out)
+{
+    if (!icp || !ref || !queries || !d_bases || !epoch_io || !d_out || world == 0 || world > 8 || rank >= world)
+    {
+        set_error("null argument or world outside [1,8]");
+        return B200ICP_ERR_BAD_ARG;
+    }
+    for (uint32_t r = 0; r < world; r++)
+        if (!d_bases[r])
+        {
+            set_error("exchange buffer of rank %u is null", r);
+            return B200ICP_ERR_BAD_ARG;
+        }
+    return run_knn_exchange(icp, ref, queries, pose6, k, max_dist, d_index_map, d_bases, world, rank, epoch_io,
+                            d_out);
+}
+
+extern "C" int b200icp_fill_no_key(b200icp_t* icp, uint64_t* d_keys, size_t n)
+{
+    if (!icp || (n && !d_keys))
+    {
+        set_error("null argument");
+        return B200ICP_ERR_BAD_ARG;
+    }
+    return run_fill_no_key(icp, d_keys, n);
+}
+
 extern "C" int b200icp_merge_keys_device(b200icp_t* icp, const uint64_t* d_parts, uint32_t parts,
                                          size_t part_stride, size_t nq, uint32_t k, uint64_t* d_out)
 {

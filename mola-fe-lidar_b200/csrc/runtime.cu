@@ -28,6 +28,8 @@ int Workspace::init(int dev)
     // (bench.py does); streams of different workspaces still run concurrently
     B2_CUDA_TRY(cudaStreamCreate(&stream));
     for (auto& e : ev) B2_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    B2_CUDA_TRY(cudaMalloc(&d_flag, 256));
+    B2_CUDA_TRY(cudaMallocHost(&h_flag, 256));
     return B200ICP_OK;
 }
 
@@ -37,6 +39,9 @@ void Workspace::destroy()
     if (stream) cudaStreamSynchronize(stream);
     if (d_scratch) cudaFree(d_scratch);
     if (h_pinned) cudaFreeHost(h_pinned);
+    if (d_flag) cudaFree(d_flag);
+    if (h_flag) cudaFreeHost(h_flag);
+    d_flag = nullptr, h_flag = nullptr;
     for (auto& e : ev)
         if (e) cudaEventDestroy(e);
     for (auto& e : prof_ev) cudaEventDestroy(e);

@@ -60,6 +60,8 @@ struct Workspace
     cudaEvent_t  ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> prof_ev;  // pairs
     uint64_t     launches = 0;
+    uint32_t*    d_flag = nullptr;  // 256 B of device memory / pinned memory for small status words
+    uint32_t*    h_flag = nullptr;
 
     int  init(int dev);
     void destroy();
@@ -150,6 +152,14 @@ int run_knn(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, co
             uint32_t k, float max_dist, uint32_t* idx_out, float* d2_out);
 int run_knn_keys(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, const double* pose6,
                  uint32_t k, float max_dist, const uint32_t* d_index_map, uint64_t* d_keys_out);
+int run_knn_keys_scatter(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, const double* pose6,
+                         uint32_t k, float max_dist, const uint32_t* d_index_map, uint64_t* const* d_gather,
+                         uint32_t world, uint32_t rank, int atomic_min);
+int run_knn_exchange(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, const double* pose6,
+                     uint32_t k, float max_dist, const uint32_t* d_index_map, uint64_t* const* d_bases,
+                     uint32_t world, uint32_t rank, uint64_t* epoch_io, uint64_t* d_out);
+int run_peer_barrier(::b200icp* ctx, uint64_t* const* d_flags, uint32_t world, uint32_t rank, uint64_t epoch);
+int run_fill_no_key(::b200icp* ctx, uint64_t* d_keys, size_t n);
 int run_merge_keys(::b200icp* ctx, const uint64_t* d_parts, uint32_t parts, size_t part_stride, size_t nq,
                    uint32_t k, uint64_t* d_out);
 int run_match(::b200icp* ctx, const b200icp_cloud* from, const b200icp_cloud* to,

@@ -153,13 +153,85 @@ class CudaShardSearch:
         self.cloud.free()
 
 
+class PeerExchange:
+    """Exchange buffers of the fused search + arg-min exchange: every rank owns
+    one device buffer that all other ranks of the node map through CUDA IPC, so
+    that the search kernel itself stores its rows into every rank's buffer over
+    NVLink (b200icp_knn_keys_scatter)."""
+
+    HEADER = 256  # bytes in front of the data: the barrier flags (one uint64 per rank)
+
+    def __init__(self, icp, rank, world, dist, nbytes):
+        self.icp, self.rank, self.world, self.nbytes = icp, rank, world, nbytes
+        self.base, handle = icp.peer_alloc(nbytes + self.HEADER)  # zero-initialised: flags start at 0
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, handle)  # also orders the zeroing before any remote access
+        else:
+            handles[0] = handle
+        self.bases = [self.base if r == rank else icp.peer_open(handles[r]) for r in range(world)]
+        self.ptrs = [b + self.HEADER for b in self.bases]
+        self.local = self.ptrs[rank]
+        self.epoch = 0
+
+    def barrier(self):
+        """all ranks of the node, through the flags in peer memory"""
+        self.epoch += 1
+        self.icp.peer_barrier(self.bases, self.rank, self.epoch)
+
+    def close(self):
+        for r, p in enumerate(self.bases):
+            if r != self.rank and p:
+                self.icp.peer_close(p)
+        self.bases, self.ptrs = [], []
+        if self.base:
+            self.icp.peer_free(self.base)
+            self.base = self.local = None
+
+
 class ShardedMap:
     """One rank's handle on a spatially sharded map: query() returns the same
-    [nq, k] packed keys on every rank."""
+    [nq, k] packed keys on every rank.  query() exchanges with NCCL collectives;
+    query_fused() lets the search kernel write into all ranks' buffers itself
+    (peer memory over NVLink) and needs only barriers."""
 
     def __init__(self, search, rank, world, dist=None):
         self.search, self.rank, self.world, self.dist = search, rank, world, dist
         self.last_exchange_bytes = 0
+        self.peers = None
+
+    def _barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def query_fused(self, queries, k, max_dist):
+        """CudaShardSearch only.  k = 1: every rank folds its key into every
+        rank's result slot with a system-scope atomicMin (search + all-reduce in
+        one kernel); k > 1: rows go to [rank][query][k] of every rank's buffer
+        (search + all-gather in one kernel) and the k-way merge kernel follows."""
+        import torch
+        s, nq = self.search, len(queries)
+        need = max(1, self.world * nq * k * 8)
+        if self.peers is None or self.peers.nbytes < need:
+            if self.peers is not None:
+                self._barrier()
+                self.peers.close()
+            self.peers = PeerExchange(s.icp, self.rank, self.world, self.dist, need)
+        px = self.peers
+        out = torch.empty((nq, k), dtype=torch.int64, device=s.device)
+        if nq == 0:
+            return out
+        # reset -> barrier -> search + scatter -> barrier -> merge: one library call, one stream
+        px.epoch = s.icp.knn_keys_exchange(s.cloud, queries, k, max_dist, px.bases, self.rank, px.epoch,
+                                           out.data_ptr(), s.index_map.data_ptr() if s.index_map.numel() else 0)
+        self.last_exchange_bytes = nq * k * 8 * (self.world - 1)
+        return out
+
+    def close(self):
+        if self.peers is not None:
+            self._barrier()
+            self.peers.close()
+            self.peers = None
 
     def query(self, queries, k, max_dist):
         import torch

@@ -74,3 +74,69 @@ def test_pair_sharding_single_rank_gather():
     rec = np.arange(12, dtype=np.float64).reshape(4, 3)
     out = M.gather_pair_results(rec, 4, 0, 1, None)
     assert np.array_equal(out, rec)
+
+
+@pytest.mark.parametrize("k", [1, 6])
+def test_fused_scatter_matches_unsharded_oracle(icp, oracle, k):
+    """b200icp_knn_keys_scatter with two virtual ranks on one GPU: each rank's
+    search writes into BOTH gather buffers (plain device buffers stand in for
+    the IPC-mapped peers); k = 1 folds with atomicMin, k = 6 merges afterwards."""
+    import torch
+    from mola_fe_lidar_b200 import multi_gpu as M
+    rng = np.random.default_rng(21)
+    themap, q = _scene(rng, 30000, 4000)
+    q[3] = np.inf
+    radius, world = 1.0, 2
+    dev = torch.device("cuda", 0)
+    owner = M.partition_by_cell(themap, world, cell=5.0, mode="interleaved")
+    qc = icp.upload(q, search_radius=radius)
+    nq = len(q)
+    bufs = [torch.full((world * nq * k,), M.NO_KEY, dtype=torch.int64, device=dev) for _ in range(world)]
+    if k > 1:
+        for b in bufs:
+            b.fill_(12345)  # stale data: the call must overwrite every row of its slice
+    torch.cuda.synchronize()
+    shards = []
+    for r in range(world):
+        mine = M.shard_indices(owner, r)
+        s = M.CudaShardSearch(icp, themap[mine], mine, radius, dev)
+        shards.append(s)
+        icp.knn_keys_scatter(s.cloud, qc, k, radius, [b.data_ptr() for b in bufs], r, s.index_map.data_ptr(),
+                             atomic_min=(k == 1))
+    torch.cuda.synchronize()
+    idx, d2 = oracle.knn(oracle.Cloud(themap), q, k, np.float32(radius) * np.float32(radius), kdtree=True)
+    for b in bufs:  # every "rank" ends up with the same data
+        if k == 1:
+            merged = b[:nq].reshape(nq, 1)
+        else:
+            merged = shards[0].merge(b.reshape(world, nq, k))
+        gi, gd = M.unpack_keys(merged.cpu().numpy().view(np.uint64))
+        assert np.array_equal(gi, idx) and np.array_equal(gd, d2)
+        assert np.all(gi[3] == 0xFFFFFFFF)
+    for s in shards:
+        s.close()
+    qc.free()
+
+
+@pytest.mark.parametrize("k", [1, 6])
+def test_one_call_exchange_single_rank(icp, oracle, k):
+    """b200icp_knn_keys_exchange with world = 1 (exchange buffer from
+    b200icp_peer_alloc, barrier flags in its header): reset, barrier, search +
+    scatter, barrier and merge in one call; twice, to exercise the epochs."""
+    import torch
+    from mola_fe_lidar_b200 import multi_gpu as M
+    rng = np.random.default_rng(33)
+    themap, q = _scene(rng, 20000, 3000)
+    dev = torch.device("cuda", 0)
+    idx_map = np.arange(len(themap), dtype=np.uint32)
+    search = M.CudaShardSearch(icp, themap, idx_map, 0.9, dev)
+    sm = M.ShardedMap(search, 0, 1, None)
+    qc = icp.upload(q, search_radius=0.9)
+    idx, d2 = oracle.knn(oracle.Cloud(themap), q, k, np.float32(0.9) * np.float32(0.9), kdtree=True)
+    for _ in range(2):
+        keys = sm.query_fused(qc, k, 0.9)
+        gi, gd = M.unpack_keys(keys.cpu().numpy().view(np.uint64))
+        assert np.array_equal(gi, idx) and np.array_equal(gd, d2)
+    assert sm.peers.epoch == 4
+    assert torch.equal(keys, sm.query(qc, k, 0.9))
+    sm.close(), qc.free(), search.close()

@@ -72,8 +72,9 @@ class ClockSampler:
     BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
            "sw_power_cap": 0x4, "hw_power_brake_slowdown": 0x80}
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period_s=0.005):
         self.idx = gpu_index
+        self.period = period_s
         self.rows, self.stop_flag, self.t = [], False, None
         self.nv, self.h, self.max_mhz = None, None, None
 
@@ -109,7 +110,7 @@ class ClockSampler:
                     self.rows.append((time.time(), float(c[0]), 0))
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(self.period)
 
     def mark(self):
         return time.time()
@@ -243,10 +244,33 @@ def knn_microbench(torch, icp, scans, poses, dev, peak):
                     "radius_m": 0.7, "kernel_ms": ms, "queries_per_s": qps,
                     "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak})
     icp.profile_enable(False)
-    for c in clouds:
+    # config C3's shape: scan-to-map registration, raw 120k-pt scans (sensor frame) against the merged map
+    from mola_fe_lidar_b200 import scene
+    rng = np.random.default_rng(17)
+    sens = [icp.upload(s) for s in scans[:6]]
+    errs, iters = [], 0
+
+    def run_c3():
+        nonlocal iters
+        for i, c in enumerate(sens):
+            truth = scene.matrix_to_pose6(poses[i])
+            guess = truth + np.r_[rng.normal(0, 0.15, 3), rng.normal(0, np.deg2rad(0.3), 1), 0.0, 0.0]
+            r = icp.align(big, c, guess)
+            errs.append(float(np.abs(r["pose"][:3] - truth[:3]).max()))
+            iters += r["n_iterations"] + 1
+
+    run_c3()
+    errs, iters = [], 0
+    ms, _ = timed(torch, run_c3)
+    c3 = {"workload": "c3_scan_to_map", "map_points": len(big), "scan_points": len(sens[0]), "registrations": len(sens),
+          "ms_per_registration": ms / len(sens), "registrations_per_s": len(sens) / (ms * 1e-3),
+          "mean_matcher_runs": iters / len(sens), "max_abs_translation_error_m": max(errs),
+          "map": "the scans of this run in one frame, merged at 0.1 m (b200icp_voxel_decimate)",
+          "guess": "true pose + N(0, 0.15 m) / N(0, 0.3 deg yaw)"}
+    for c in clouds + sens:
         c.free()
     big.free()
-    return out
+    return out, c3
 
 
 def batch_lc(torch, dist, capi, lidar_odometry, scans, rank, world, local_rank, dev, pairs_per_gpu, mc=10):
@@ -376,7 +400,7 @@ def sharded_knn(torch, dist, capi, scans, poses, rank, world, local_rank, dev, m
             case["fused_peer_memory"] = {"ms": fms, "queries_per_s": len(queries) / (fms * 1e-3),
                                          "identical_to_nccl_path": same,
                                          "how": "search + atomicMin_system into every rank's slot" if k == 1
-                                         else "search + P2P row stores into every rank's buffer, then the merge kernel"}
+                                         else "search + P2P row stores to the owner of each query, owner merges and stores the merged rows to every rank"}
         except Exception as e:
             case["fused_peer_memory"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         out["cases"].append(case)
@@ -436,7 +460,9 @@ def run_b200(args, rank, world, local_rank):
         return r
 
     total = args.warmup + args.steps
-    sampler = ClockSampler(local_rank)
+    # rank 0 samples its GPU every 5 ms; the other ranks every 50 ms (NVML calls of many processes
+    # at a high rate get in the way of each other's kernel launches)
+    sampler = ClockSampler(local_rank, 0.005 if rank == 0 else 0.05)
     sampler.start()
     for s in range(args.warmup):
         step_value(s)
@@ -515,7 +541,7 @@ def run_b200(args, rank, world, local_rank):
     if not args.no_extras:
         try:
             if rank == 0:
-                extras["knn"] = knn_microbench(torch, icp, scans, poses, dev, peak)
+                extras["knn"], extras["scan_to_map"] = knn_microbench(torch, icp, scans, poses, dev, peak)
             shared_scans, shared_poses = (scans, poses) if world == 1 else make_scans(1)
             extras["batch_lc"] = batch_lc(torch, dist, capi, lidar_odometry, shared_scans, rank, world, local_rank,
                                           dev, args.pairs_per_gpu)

@@ -217,12 +217,18 @@ int b200icp_peer_close(b200icp_t* icp, void* d_peer_ptr);
 int b200icp_peer_barrier(b200icp_t* icp, uint64_t* const* d_flags, uint32_t world, uint32_t rank,
                          uint64_t epoch);
 /* The whole sharded query in ONE call on one stream with one host
- * synchronisation: reset, barrier, search with scatter into every rank's buffer
- * (atomicMin for k = 1), barrier, merge into d_out[nq*k] (device).  d_bases[r]:
- * rank r's exchange buffer as mapped here (b200icp_peer_alloc / _open), at least
- * 256 + world*nq*k*8 bytes: barrier flags in the first 256 bytes, keys after
- * them.  *epoch_io: the barrier epoch, same start value (0) on every rank,
- * advanced by the call. */
+ * synchronisation, result in d_out[nq*k] (device).
+ *   k = 1: reset, barrier, search folding its key into slot [q] of every rank's
+ *          buffer (atomicMin_system), barrier.
+ *   k > 1: barrier, search storing the row of query q into the buffer of the
+ *          rank that OWNS q (q / ceil(nq/world)), barrier, the owner merges its
+ *          slice and stores the merged rows into every rank's result region,
+ *          barrier (reduce-scatter + all-gather, both as P2P stores from the
+ *          kernels: 2*nq*k keys of traffic per rank).
+ * d_bases[r]: rank r's exchange buffer as mapped here (b200icp_peer_alloc /
+ * _open), at least 256 + 2*world*ceil(nq/world)*k*8 bytes: barrier flags in
+ * the first 256 bytes, keys after them.  *epoch_io: the barrier epoch, same
+ * start value (0) on every rank, advanced by the call. */
 int b200icp_knn_keys_exchange(b200icp_t* icp, const b200icp_cloud_t* ref, const b200icp_cloud_t* queries,
                               const double* pose6, uint32_t k, float max_dist,
                               const uint32_t* d_index_map, uint64_t* const* d_bases, uint32_t world,

@@ -167,36 +167,65 @@ struct KeyWriter
 // [rank][query][k] of every buffer (search + all-gather in one kernel); with
 // `amin` (k = 1) the key is folded into slot [query] of every buffer with a
 // system-scope atomicMin (search + all-reduce(MIN) in one kernel).
+// `per` > 0 (reduce-scatter form): the row of query q goes ONLY to the rank
+// that owns q (owner = q / per), at [rank][q - owner * per][k] of its buffer;
+// the owner merges its slice and broadcasts the merged rows
+// (merge_scatter_kernel) -- 2 x nq x k keys of traffic per rank instead of
+// world x nq x k.
 struct KeyScatter
 {
     uint64_t*       peer[8];
     const uint32_t* map;
-    uint32_t        k, world, rank, nq, amin;
+    uint32_t        k, world, rank, nq, amin, per;
     template <int K>
     __device__ __forceinline__ void operator()(JobDev&, bool has, uint32_t, uint32_t orig,
                                                const uint64_t (&key)[K], uint64_t sent) const
     {
         if (!has) return;
+        uint64_t v[K];
 #pragma unroll
         for (int i = 0; i < K; i++)
-            if ((uint32_t)i < k)
+        {
+            v[i] = B200ICP_NO_KEY;
+            if ((uint32_t)i < k && key[i] != sent)
             {
-                uint64_t v = B200ICP_NO_KEY;
-                if (key[i] != sent)
-                {
-                    const uint32_t li = key_idx(key[i]);
-                    v = (key[i] & 0xFFFFFFFF00000000ull) | (uint64_t)(map ? __ldg(map + li) : li);
-                }
-                if (amin)
-                {
-                    if (v != B200ICP_NO_KEY)
-                        for (uint32_t r = 0; r < world; r++)
-                            atomicMin_system(reinterpret_cast<unsigned long long*>(peer[r]) + orig,
-                                             (unsigned long long)v);
-                }
-                else
-                    for (uint32_t r = 0; r < world; r++) peer[r][((size_t)rank * nq + orig) * k + i] = v;
+                const uint32_t li = key_idx(key[i]);
+                v[i] = (key[i] & 0xFFFFFFFF00000000ull) | (uint64_t)(map ? __ldg(map + li) : li);
             }
+        }
+        if (amin)
+        {
+            if (v[0] != B200ICP_NO_KEY)
+                for (uint32_t r = 0; r < world; r++)
+                    atomicMin_system(reinterpret_cast<unsigned long long*>(peer[r]) + orig, (unsigned long long)v[0]);
+            return;
+        }
+        if (per)
+        {
+            const uint32_t owner = orig / per;
+            uint64_t*      dst = peer[owner] + ((size_t)rank * per + (orig - owner * per)) * k;
+            store_row<K>(dst, v);
+            return;
+        }
+        for (uint32_t r = 0; r < world; r++) store_row<K>(peer[r] + ((size_t)rank * nq + orig) * k, v);
+    }
+    // k keys to dst: 16-byte stores when the row allows it (k even)
+    template <int K>
+    __device__ __forceinline__ void store_row(uint64_t* dst, const uint64_t (&v)[K]) const
+    {
+        if ((k & 1u) == 0 && (K & 1) == 0)
+        {
+#pragma unroll
+            for (int i = 0; i < K; i += 2)
+                if ((uint32_t)i < k)
+                    *reinterpret_cast<ulonglong2*>(dst + i) = make_ulonglong2(v[i], v[i + 1]);
+        }
+        else
+        {
+#pragma unroll
+            for (int i = 0; i < K; i++)
+                if ((uint32_t)i < k) dst[i] = v[i];
+        }
     }
 };
 
@@ -1728,6 +1757,56 @@ int run_knn(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, co
     return B200ICP_OK;
 }
 
+// Owner side of the reduce-scatter exchange: thread ql merges the `world` lists
+// of local query ql (global q = rank * per + ql) and stores the merged row into
+// the result region of EVERY rank (P2P stores over NVLink).
+struct PeerPtrs
+{
+    uint64_t* p[8];
+};
+template <int K>
+__global__ void __launch_bounds__(256)
+    merge_scatter_kernel(const uint64_t* __restrict__ gather, uint32_t world, uint32_t rank, uint32_t per, uint32_t nq,
+                         uint32_t k, PeerPtrs result)
+{
+    const uint32_t ql = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ql >= per) return;
+    const size_t q = (size_t)rank * per + ql;
+    if (q >= nq) return;
+    uint64_t key[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) key[i] = ~0ull;
+    for (uint32_t p = 0; p < world; p++)
+    {
+        const uint64_t* row = gather + ((size_t)p * per + ql) * k;
+        for (uint32_t i = 0; i < k; i++)
+        {
+            const uint64_t kk = row[i];  // written by peers: no read-only path
+            if (!(kk < key[K - 1])) break;
+            topk_insert<K>(key, kk);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < K; i++)
+        if (key[i] == ~0ull) key[i] = B200ICP_NO_KEY;
+    for (uint32_t r = 0; r < world; r++)
+    {
+        uint64_t* dst = result.p[r] + q * k;
+        if ((k & 1u) == 0 && (K & 1) == 0)
+        {
+#pragma unroll
+            for (int i = 0; i < K; i += 2)
+                if ((uint32_t)i < k) *reinterpret_cast<ulonglong2*>(dst + i) = make_ulonglong2(key[i], key[i + 1]);
+        }
+        else
+        {
+#pragma unroll
+            for (int i = 0; i < K; i++)
+                if ((uint32_t)i < k) dst[i] = key[i];
+        }
+    }
+}
+
 int run_knn_keys(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, const double* pose6,
                  uint32_t k, float max_dist, const uint32_t* d_index_map, uint64_t* d_keys_out)
 {
@@ -1780,7 +1859,8 @@ int run_knn_keys(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* 
 // enqueues the scatter search on ws->stream (no host synchronisation)
 static int enqueue_scatter(::b200icp* ctx, Workspace* ws, const b200icp_cloud* ref, const b200icp_cloud* q,
                            const double* pose6, uint32_t k, float max_dist, const uint32_t* d_index_map,
-                           uint64_t* const* d_gather, uint32_t world, uint32_t rank, int atomic_min, bool time_it)
+                           uint64_t* const* d_gather, uint32_t world, uint32_t rank, int atomic_min, uint32_t per,
+                           bool time_it)
 {
     if (k < 1 || k > B200ICP_MAX_KNN || !(max_dist > 0) || !std::isfinite(max_dist) || (atomic_min && k != 1))
     {
@@ -1797,13 +1877,15 @@ static int enqueue_scatter(::b200icp* ctx, Workspace* ws, const b200icp_cloud* r
     memset(&w, 0, sizeof(w));
     for (uint32_t r = 0; r < world; r++) w.peer[r] = d_gather[r];
     w.map = d_index_map, w.k = k, w.world = world, w.rank = rank, w.nq = (uint32_t)nq, w.amin = atomic_min ? 1u : 0u;
+    w.per = per;
     if (!atomic_min)
     {
         // rows of non-finite queries are never visited by the search: this rank's
         // slice of EVERY buffer is reset first
+        const size_t rows = per ? per : nq;
         for (uint32_t r = 0; r < world; r++)
-            fill_u64_kernel<<<(int)((nq * k + 255) / 256), 256, 0, s>>>(d_gather[r] + (size_t)rank * nq * k, nq * k,
-                                                                          B200ICP_NO_KEY);
+            fill_u64_kernel<<<(int)((rows * k + 255) / 256), 256, 0, s>>>(d_gather[r] + (size_t)rank * rows * k,
+                                                                            rows * k, B200ICP_NO_KEY);
         ws->launches += world;
     }
     if (time_it)
@@ -1844,7 +1926,7 @@ int run_knn_keys_scatter(::b200icp* ctx, const b200icp_cloud* ref, const b200icp
     if (!L.ws) return B200ICP_ERR_CUDA;
     const bool prof = ctx->profile_on;
     if (int r = enqueue_scatter(ctx, L.ws, ref, q, pose6, k, max_dist, d_index_map, d_gather, world, rank,
-                                atomic_min, prof))
+                                atomic_min, 0u, prof))
         return r;
     B2_CUDA_TRY(cudaStreamSynchronize(L.ws->stream));
     if (prof) return account_knn_time(ctx, L.ws, q->n);
@@ -1933,39 +2015,53 @@ int run_knn_exchange(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_clo
         f.p[r] = d_bases[r];
         data[r] = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(d_bases[r]) + kPeerHeader);
     }
-    const bool amin = (k == 1);
-    const bool prof = ctx->profile_on;
-    const uint64_t e0 = *epoch_io + 1, e1 = *epoch_io + 2;
+    const bool     amin = (k == 1);
+    const bool     prof = ctx->profile_on;
+    const uint32_t per = (uint32_t)((nq + world - 1) / world);  // queries owned by one rank
+    uint64_t       epoch = *epoch_io;
+    auto barrier = [&]() {
+        peer_barrier_kernel<<<1, 32, 0, s>>>(f, world, rank, (unsigned long long)++epoch, ws->d_flag);
+        ws->launches++;
+    };
     B2_CUDA_TRY(cudaMemsetAsync(ws->d_flag, 0, sizeof(uint32_t), s));
     if (amin)
-    {  // own result slots back to "no neighbour" before anybody folds into them
+    {
+        // k = 1: every rank folds its key into every rank's slot [q] (atomicMin): search + all-reduce
         fill_u64_kernel<<<(int)((nq + 255) / 256), 256, 0, s>>>(data[rank], nq, B200ICP_NO_KEY);
         ws->launches++;
+        barrier();
+        if (int r = enqueue_scatter(ctx, ws, ref, q, pose6, k, max_dist, d_index_map, data, world, rank, 1, 0u, prof))
+            return r;
+        barrier();
+        B2_CUDA_TRY(cudaMemcpyAsync(d_out, data[rank], nq * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
     }
-    peer_barrier_kernel<<<1, 32, 0, s>>>(f, world, rank, (unsigned long long)e0, ws->d_flag);
-    ws->launches++;
-    if (int r = enqueue_scatter(ctx, ws, ref, q, pose6, k, max_dist, d_index_map, data, world, rank, amin ? 1 : 0,
-                                prof))
-        return r;
-    peer_barrier_kernel<<<1, 32, 0, s>>>(f, world, rank, (unsigned long long)e1, ws->d_flag);
-    ws->launches++;
+    else
     {
-        const int      blocks = (int)((nq + 255) / 256);
-        const uint32_t parts = amin ? 1u : world;
-        if (k == 1)
-            merge_keys_kernel<1><<<blocks, 256, 0, s>>>(data[rank], parts, nq * k, nq, k, d_out);
-        else if (k <= 4)
-            merge_keys_kernel<4><<<blocks, 256, 0, s>>>(data[rank], parts, nq * k, nq, k, d_out);
+        // k > 1, reduce-scatter form.  Buffer: gather region [world][per][k], then result region [world*per][k].
+        // 1. rows of query q go to owner(q) only; 2. the owner merges its slice and stores the merged rows into
+        // every rank's result region; 3. the local result region is the answer.
+        PeerPtrs res;
+        memset(&res, 0, sizeof(res));
+        for (uint32_t r = 0; r < world; r++) res.p[r] = data[r] + (size_t)world * per * k;
+        barrier();
+        if (int r = enqueue_scatter(ctx, ws, ref, q, pose6, k, max_dist, d_index_map, data, world, rank, 0, per, prof))
+            return r;
+        barrier();
+        const int blocks = (int)((per + 255) / 256);
+        if (k <= 4)
+            merge_scatter_kernel<4><<<blocks, 256, 0, s>>>(data[rank], world, rank, per, (uint32_t)nq, k, res);
         else if (k <= 6)
-            merge_keys_kernel<6><<<blocks, 256, 0, s>>>(data[rank], parts, nq * k, nq, k, d_out);
+            merge_scatter_kernel<6><<<blocks, 256, 0, s>>>(data[rank], world, rank, per, (uint32_t)nq, k, res);
         else
-            merge_keys_kernel<8><<<blocks, 256, 0, s>>>(data[rank], parts, nq * k, nq, k, d_out);
+            merge_scatter_kernel<8><<<blocks, 256, 0, s>>>(data[rank], world, rank, per, (uint32_t)nq, k, res);
         ws->launches++;
+        barrier();
+        B2_CUDA_TRY(cudaMemcpyAsync(d_out, res.p[rank], nq * k * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
     }
     B2_CUDA_TRY(cudaMemcpyAsync(ws->h_flag, ws->d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     B2_CUDA_TRY(cudaStreamSynchronize(s));
     B2_CUDA_TRY(cudaGetLastError());
-    *epoch_io = e1;
+    *epoch_io = epoch;
     if (*ws->h_flag)
     {
         set_error("peer barrier timed out on rank %u: a rank of the node did not arrive", rank);

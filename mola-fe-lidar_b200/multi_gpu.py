@@ -207,11 +207,14 @@ class ShardedMap:
     def query_fused(self, queries, k, max_dist):
         """CudaShardSearch only.  k = 1: every rank folds its key into every
         rank's result slot with a system-scope atomicMin (search + all-reduce in
-        one kernel); k > 1: rows go to [rank][query][k] of every rank's buffer
-        (search + all-gather in one kernel) and the k-way merge kernel follows."""
+        one kernel); k > 1: the row of a query goes to the rank that owns the
+        query (search + reduce-scatter in one kernel), the owner merges its
+        slice and stores the merged rows into every rank's buffer (merge +
+        all-gather in one kernel)."""
         import torch
         s, nq = self.search, len(queries)
-        need = max(1, self.world * nq * k * 8)
+        per = (nq + self.world - 1) // self.world
+        need = max(8, 2 * self.world * per * k * 8)  # gather region + result region (see b200icp_knn_keys_exchange)
         if self.peers is None or self.peers.nbytes < need:
             if self.peers is not None:
                 self._barrier()

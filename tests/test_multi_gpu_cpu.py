@@ -115,7 +115,11 @@ def test_pack_unpack_and_merge_keys():
 @pytest.mark.timeout(300)
 def test_sharded_map_and_pair_sharding_world2(tmp_path, oracle):
     import torch.multiprocessing as mp
-    world, port = 2, 29500 + (os.getpid() % 2000)
+    import socket
+    with socket.socket() as sk:  # a free port: suites may run side by side
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    world = 2
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     r0 = np.load(tmp_path / "rank0.npz")
     r1 = np.load(tmp_path / "rank1.npz")

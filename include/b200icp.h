@@ -218,8 +218,10 @@ int b200icp_peer_barrier(b200icp_t* icp, uint64_t* const* d_flags, uint32_t worl
                          uint64_t epoch);
 /* The whole sharded query in ONE call on one stream with one host
  * synchronisation, result in d_out[nq*k] (device).
- *   k = 1: reset, barrier, search folding its key into slot [q] of every rank's
- *          buffer (atomicMin_system), barrier.
+ *   k = 1: reset, barrier, search folding its key into the slot of query q in
+ *          the buffer of the rank that OWNS q (atomicMin_system over NVLink),
+ *          barrier, the owner stores its slice into every rank's result region,
+ *          barrier.
  *   k > 1: barrier, search storing the row of query q into the buffer of the
  *          rank that OWNS q (q / ceil(nq/world)), barrier, the owner merges its
  *          slice and stores the merged rows into every rank's result region,

@@ -195,9 +195,16 @@ struct KeyScatter
         }
         if (amin)
         {
-            if (v[0] != B200ICP_NO_KEY)
-                for (uint32_t r = 0; r < world; r++)
-                    atomicMin_system(reinterpret_cast<unsigned long long*>(peer[r]) + orig, (unsigned long long)v[0]);
+            if (v[0] == B200ICP_NO_KEY) return;
+            if (per)
+            {  // only the owner of the query keeps the minimum; it broadcasts its slice afterwards
+                const uint32_t owner = orig / per;
+                atomicMin_system(reinterpret_cast<unsigned long long*>(peer[owner]) + (orig - owner * per),
+                                 (unsigned long long)v[0]);
+                return;
+            }
+            for (uint32_t r = 0; r < world; r++)
+                atomicMin_system(reinterpret_cast<unsigned long long*>(peer[r]) + orig, (unsigned long long)v[0]);
             return;
         }
         if (per)
@@ -245,7 +252,7 @@ struct HitCounter
 };
 
 // Tile sweep (sweep_search.cuh): one CTA of WPI warps per item, items taken
-// grid-stride.  gate != 0: skip finished jobs and iterations at which the
+// grid-stride.  gate 1: skip finished jobs and iterations at which the
 // matcher does not run.
 template <int K, int WPI, class Epi>
 __global__ void __launch_bounds__(32 * WPI)
@@ -253,7 +260,8 @@ __global__ void __launch_bounds__(32 * WPI)
                         float cap_d2, int gate, Epi epi)
 {
     JobDev& J = jobs[blockIdx.y];
-    if (gate && (J.status != 0 || !matcher_active(P, J.iter))) return;
+    if (gate == 1 && (J.status != 0 || !matcher_active(P, J.iter))) return;  // matcher: running jobs only
+    if (gate == 2 && (J.status == 0 || J.evaluated != 0)) return;            // quality: finished, once
     const CloudView cvL = clouds[J.to_cloud];
     const CloudView cvG = clouds[J.from_cloud];
 
@@ -394,7 +402,8 @@ __global__ void __launch_bounds__(kChunk)
                        float cap_d2, int gate, Epi epi)
 {
     JobDev& J = jobs[blockIdx.y];
-    if (gate && (J.status != 0 || !matcher_active(P, J.iter))) return;
+    if (gate == 1 && (J.status != 0 || !matcher_active(P, J.iter))) return;  // matcher: running jobs only
+    if (gate == 2 && (J.status == 0 || J.evaluated != 0)) return;            // quality: finished, once
     const CloudView cvL = clouds[J.to_cloud];
     const CloudView cvG = clouds[J.from_cloud];
     __shared__ SearchSmem sm;
@@ -1105,11 +1114,19 @@ __global__ void __launch_bounds__(kSolveThreads)
 // mp2p_icp::covariance (row P / A.9): forward-difference Jacobian of the
 // stacked residuals wrt (x,y,z,yaw,pitch,roll) at the solution, H = J^T J,
 // cov = H^-1.  With linear-in-theta residuals J^T J = dTheta^T A dTheta.
+// Runs right after the quality search of the same batch, on finished jobs
+// that have not been evaluated yet, and marks them evaluated (the quality count
+// must be taken once).
 __global__ void __launch_bounds__(64) covariance_kernel(JobDev* __restrict__ jobs, IcpDevParams P)
 {
     JobDev&   J = jobs[blockIdx.x];
     const int tid = threadIdx.x;
     __shared__ double sA[144], sD[72], sH[36];
+    __shared__ int    s_go;
+    if (tid == 0) s_go = (J.status != 0 && J.evaluated == 0) ? 1 : 0;
+    __syncthreads();
+    if (!s_go) return;
+    if (tid == 0) J.evaluated = 1;
     const bool p2p = (P.matcher_kind == B200ICP_MATCHER_POINTS_DISTANCE);
     if (J.n_pairings == 0)
     {
@@ -1468,6 +1485,14 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
     // A single registration (the odometry call) therefore sizes its first batch
     // from the previous call on this ICP object -- consecutive scans need about
     // the same number of iterations -- and checks it right away.
+    cudaError_t eval_err = cudaSuccess;
+    auto evaluate = [&]() {
+        launch_search_k<1>(ctx, ws, max_points, n, d_clouds, d_jobs, D, D.q_thr2, 2, HitCounter{D.q_thr2});
+        covariance_kernel<<<(unsigned)n, 64, 0, s>>>(d_jobs, D);
+        ws->launches++;
+        const cudaError_t e = cudaMemcpyAsync(h_jobs, d_jobs, n * sizeof(JobDev), cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) eval_err = e;
+    };
     const uint32_t kBatch = 4;
     const bool     predict = (n == 1) && ctx->expected_runs.load() > 0;
     const uint32_t first = predict ? (uint32_t)std::min(std::max(ctx->expected_runs.load() + 1, 2), 24) : kBatch;
@@ -1500,6 +1525,11 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
             }
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 3], s));
         }
+        // Single registration: the evaluation of the job if this batch has finished it
+        // (QualityEvaluator_PairedRatio: one more search, k = 1, its own radius; then the covariance) and the
+        // job record are enqueued without waiting for the host to learn that it finished -- an unfinished job
+        // makes these launches exit at once.  Saves one host round trip per registration.
+        if (n == 1) evaluate();
         // the host stays one batch ahead of the device: it only looks at the
         // active-job counter of the PREVIOUS batch, so the stream never drains
         const int slot = batch & 1;
@@ -1518,11 +1548,8 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
         }
         batch++;
     }
-    // QualityEvaluator_PairedRatio: one more search (k = 1, its own radius) on every job
-    launch_search_k<1>(ctx, ws, max_points, n, d_clouds, d_jobs, D, D.q_thr2, 0, HitCounter{D.q_thr2});
-    covariance_kernel<<<(unsigned)n, 64, 0, s>>>(d_jobs, D);
-    ws->launches++;
-    B2_CUDA_TRY(cudaMemcpyAsync(h_jobs, d_jobs, n * sizeof(JobDev), cudaMemcpyDeviceToHost, s));
+    if (n != 1) evaluate();  // batches: once, after the last job has finished
+    B2_CUDA_TRY(eval_err);
     B2_CUDA_TRY(cudaStreamSynchronize(s));
     B2_CUDA_TRY(cudaGetLastError());
 
@@ -1766,8 +1793,8 @@ struct PeerPtrs
 };
 template <int K>
 __global__ void __launch_bounds__(256)
-    merge_scatter_kernel(const uint64_t* __restrict__ gather, uint32_t world, uint32_t rank, uint32_t per, uint32_t nq,
-                         uint32_t k, PeerPtrs result)
+    merge_scatter_kernel(const uint64_t* __restrict__ gather, uint32_t nparts, uint32_t world, uint32_t rank,
+                         uint32_t per, uint32_t nq, uint32_t k, PeerPtrs result)
 {
     const uint32_t ql = blockIdx.x * blockDim.x + threadIdx.x;
     if (ql >= per) return;
@@ -1776,7 +1803,7 @@ __global__ void __launch_bounds__(256)
     uint64_t key[K];
 #pragma unroll
     for (int i = 0; i < K; i++) key[i] = ~0ull;
-    for (uint32_t p = 0; p < world; p++)
+    for (uint32_t p = 0; p < nparts; p++)
     {
         const uint64_t* row = gather + ((size_t)p * per + ql) * k;
         for (uint32_t i = 0; i < k; i++)
@@ -2024,40 +2051,44 @@ int run_knn_exchange(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_clo
         ws->launches++;
     };
     B2_CUDA_TRY(cudaMemsetAsync(ws->d_flag, 0, sizeof(uint32_t), s));
+    // Buffer: gather region [world][per][k] (k = 1: [per], one folded slot per owned query), then the result
+    // region [world*per][k].
+    PeerPtrs res;
+    memset(&res, 0, sizeof(res));
+    for (uint32_t r = 0; r < world; r++) res.p[r] = data[r] + (size_t)world * per * k;
+    const int mblocks = (int)((per + 255) / 256);
     if (amin)
     {
-        // k = 1: every rank folds its key into every rank's slot [q] (atomicMin): search + all-reduce
-        fill_u64_kernel<<<(int)((nq + 255) / 256), 256, 0, s>>>(data[rank], nq, B200ICP_NO_KEY);
+        // k = 1: every rank folds its key into the OWNER's slot of the query (atomicMin over NVLink: search +
+        // reduce-scatter(MIN) in one kernel); the owner then stores its slice into every rank's result region
+        fill_u64_kernel<<<mblocks, 256, 0, s>>>(data[rank], per, B200ICP_NO_KEY);
         ws->launches++;
         barrier();
-        if (int r = enqueue_scatter(ctx, ws, ref, q, pose6, k, max_dist, d_index_map, data, world, rank, 1, 0u, prof))
+        if (int r = enqueue_scatter(ctx, ws, ref, q, pose6, k, max_dist, d_index_map, data, world, rank, 1, per, prof))
             return r;
         barrier();
-        B2_CUDA_TRY(cudaMemcpyAsync(d_out, data[rank], nq * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+        merge_scatter_kernel<1><<<mblocks, 256, 0, s>>>(data[rank], 1u, world, rank, per, (uint32_t)nq, k, res);
+        ws->launches++;
+        barrier();
     }
     else
     {
-        // k > 1, reduce-scatter form.  Buffer: gather region [world][per][k], then result region [world*per][k].
-        // 1. rows of query q go to owner(q) only; 2. the owner merges its slice and stores the merged rows into
-        // every rank's result region; 3. the local result region is the answer.
-        PeerPtrs res;
-        memset(&res, 0, sizeof(res));
-        for (uint32_t r = 0; r < world; r++) res.p[r] = data[r] + (size_t)world * per * k;
+        // k > 1, reduce-scatter form: 1. rows of query q go to owner(q) only; 2. the owner merges its slice and
+        // stores the merged rows into every rank's result region; 3. the local result region is the answer.
         barrier();
         if (int r = enqueue_scatter(ctx, ws, ref, q, pose6, k, max_dist, d_index_map, data, world, rank, 0, per, prof))
             return r;
         barrier();
-        const int blocks = (int)((per + 255) / 256);
         if (k <= 4)
-            merge_scatter_kernel<4><<<blocks, 256, 0, s>>>(data[rank], world, rank, per, (uint32_t)nq, k, res);
+            merge_scatter_kernel<4><<<mblocks, 256, 0, s>>>(data[rank], world, world, rank, per, (uint32_t)nq, k, res);
         else if (k <= 6)
-            merge_scatter_kernel<6><<<blocks, 256, 0, s>>>(data[rank], world, rank, per, (uint32_t)nq, k, res);
+            merge_scatter_kernel<6><<<mblocks, 256, 0, s>>>(data[rank], world, world, rank, per, (uint32_t)nq, k, res);
         else
-            merge_scatter_kernel<8><<<blocks, 256, 0, s>>>(data[rank], world, rank, per, (uint32_t)nq, k, res);
+            merge_scatter_kernel<8><<<mblocks, 256, 0, s>>>(data[rank], world, world, rank, per, (uint32_t)nq, k, res);
         ws->launches++;
         barrier();
-        B2_CUDA_TRY(cudaMemcpyAsync(d_out, res.p[rank], nq * k * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
     }
+    B2_CUDA_TRY(cudaMemcpyAsync(d_out, res.p[rank], nq * k * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
     B2_CUDA_TRY(cudaMemcpyAsync(ws->h_flag, ws->d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     B2_CUDA_TRY(cudaStreamSynchronize(s));
     B2_CUDA_TRY(cudaGetLastError());

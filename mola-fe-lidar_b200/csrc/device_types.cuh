@@ -80,7 +80,7 @@ struct JobDev
     uint32_t inner_iters_total;
     uint32_t pair_base;    // first row of this job in the launch's neighbour / pair buffers
     uint32_t next_item;    // work counter of the search stage (reset by the solver)
-    uint32_t pad_;
+    uint32_t evaluated;    // quality + covariance taken (once, after the job finished)
 };
 
 struct IcpDevParams

@@ -205,12 +205,13 @@ class ShardedMap:
             self.dist.barrier()
 
     def query_fused(self, queries, k, max_dist):
-        """CudaShardSearch only.  k = 1: every rank folds its key into every
-        rank's result slot with a system-scope atomicMin (search + all-reduce in
-        one kernel); k > 1: the row of a query goes to the rank that owns the
-        query (search + reduce-scatter in one kernel), the owner merges its
-        slice and stores the merged rows into every rank's buffer (merge +
-        all-gather in one kernel)."""
+        """CudaShardSearch only.  The kernels store straight into the ranks'
+        exchange buffers over NVLink.  k = 1: every rank folds its key into the
+        slot of the query on the rank that owns the query (system-scope
+        atomicMin: search + reduce-scatter in one kernel), the owner stores its
+        slice into every rank's buffer; k > 1: the row of a query goes to its
+        owner, the owner merges its slice and stores the merged rows into every
+        rank's buffer (merge + all-gather in one kernel)."""
         import torch
         s, nq = self.search, len(queries)
         per = (nq + self.world - 1) // self.world

@@ -509,6 +509,8 @@ def run_b200(args, rank, world, local_rank):
     # the additive key b200_extra_edge_checks so that every timed scan costs
     # exactly one consecutive-scan registration -- the unit `value` and the
     # reference arm count; `e2e_full_module` below runs the module as shipped.
+    replays = {"n": 0}
+
     def run_module(extra_yaml, steps, warm, voxel=None):
         # additive key b200_device: this rank's GPU
         lo = lidar_odometry.LidarOdometry(
@@ -534,6 +536,7 @@ def run_b200(args, rank, world, local_rank):
         ms = e2.elapsed_time(e3)
         st = lo.state()
         prof_mod = lo.profile()
+        replays["n"] = sum(capi.ICP.profile_of_handle(lo.icp_handle(kind))["graph_replays"] for kind in (0, 1, 2))
         lo.close()
         n_all = max(st["n_processed"], 1)
         sections = {k.replace("doProcessNewObservation.", ""): [round(v[1] / max(v[0], 1) * 1e3, 3), round(v[2] * 1e3, 3)]
@@ -543,6 +546,7 @@ def run_b200(args, rank, world, local_rank):
             int(st["n_keyframes"])
 
     ms_e2e, e2e_regs, e2e_scans, _ = run_module("  b200_extra_edge_checks: false\n", args.steps, args.warmup)
+    e2e_graph_replays = int(replays["n"])
     ms_full, full_regs, full_scans, full_kfs = run_module("", args.steps, max(args.warmup, 12))
     # C2's decimated variant: the voxel filter kitti-default.yaml hints at (1.0 m) in front of the same ICP
     ms_dec, dec_regs, _, _ = run_module("  b200_extra_edge_checks: false\n", args.steps, args.warmup, voxel=1.0)
@@ -604,6 +608,7 @@ def run_b200(args, rank, world, local_rank):
                          "note": "working set is L2-resident; the kernel is issue/latency bound, see DESIGN.md"},
             "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": n_pts * 12,
                     "d2h_bytes_per_step": 1128, "ms_per_step": ms_e2e_max / max(e2e_regs / world, 1),
+                    "cuda_graph_replays_rank0": e2e_graph_replays,
                     "api": "LidarOdometry.onNewObservation (b200lo_process_observation), pinned host SoA; "
                            "b200_extra_edge_checks: false (one consecutive-scan registration per scan)"},
             "e2e_full_module": {"registrations_per_s": float(u[2]) / (ms_full_max * 1e-3),

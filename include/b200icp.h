@@ -113,6 +113,7 @@ typedef struct b200icp_profile
     uint64_t total_kernel_launches; /* every kernel this library launched */
     uint64_t fit_launches;    /* plane fit + gates + moments kernel */
     double   fit_ms;
+    uint64_t graph_replays;   /* single registrations whose first batch ran as one CUDA-graph launch */
 } b200icp_profile_t;
 
 typedef struct b200icp       b200icp_t;       /* the mp2p_icp::ICP object + its Parameters */

@@ -80,6 +80,7 @@ class Profile(C.Structure):
         ("voxel_launches", C.c_uint64), ("voxel_ms", C.c_double), ("voxel_points", C.c_uint64),
         ("total_kernel_launches", C.c_uint64),
         ("fit_launches", C.c_uint64), ("fit_ms", C.c_double),
+        ("graph_replays", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -394,6 +395,13 @@ class ICP:
     def profile(self):
         p = Profile()
         lib().b200icp_profile_get(self.h, C.byref(p))
+        return p.as_dict()
+
+    @staticmethod
+    def profile_of_handle(raw_handle):
+        """Profile counters of a raw b200icp_t* (e.g. LidarOdometry.icp_handle())."""
+        p = Profile()
+        lib().b200icp_profile_get(raw_handle, C.byref(p))
         return p.as_dict()
 
     def synchronize(self):

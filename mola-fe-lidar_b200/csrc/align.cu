@@ -1237,6 +1237,7 @@ struct SearchConfig
 {
     bool sweep = false;
     int  wpi = 0;  // 0 = automatic
+    bool graphs = true;  // B200ICP_GRAPH=0: no CUDA-graph replay of single registrations
 };
 static const SearchConfig& search_config()
 {
@@ -1244,6 +1245,7 @@ static const SearchConfig& search_config()
         SearchConfig c;
         if (const char* s = getenv("B200ICP_SEARCH")) c.sweep = (strcmp(s, "sweep") == 0);
         if (const char* w = getenv("B200ICP_WPI")) c.wpi = atoi(w);
+        if (const char* g = getenv("B200ICP_GRAPH")) c.graphs = atoi(g) != 0;
         return c;
     }();
     return cfg;
@@ -1468,10 +1470,13 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
     memcpy(h_jobs, hjobs.data(), n * sizeof(JobDev));
     h_flags[0] = h_flags[1] = 0xFFFFFFFFu;
     h_flags[2] = (uint32_t)n;
-    B2_CUDA_TRY(cudaMemcpyAsync(d_clouds, h_views, views.size() * sizeof(CloudView),
-                                cudaMemcpyHostToDevice, s));
-    B2_CUDA_TRY(cudaMemcpyAsync(d_jobs, h_jobs, n * sizeof(JobDev), cudaMemcpyHostToDevice, s));
-    B2_CUDA_TRY(cudaMemcpyAsync(d_active, h_flags + 2, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    cudaError_t setup_err = cudaSuccess;
+    auto enqueue_setup = [&]() {
+        cudaError_t e = cudaMemcpyAsync(d_clouds, h_views, views.size() * sizeof(CloudView), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_jobs, h_jobs, n * sizeof(JobDev), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_active, h_flags + 2, sizeof(uint32_t), cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) setup_err = e;
+    };
 
     const bool prof = ctx->profile_on;
     if (prof)
@@ -1498,6 +1503,69 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
     const uint32_t first = predict ? (uint32_t)std::min(std::max(ctx->expected_runs.load() + 1, 2), 24) : kBatch;
     uint32_t       enq = 0, batch = 0;
     bool           finished = false;
+
+    // A single predicted registration without profiling replays its first batch -- job upload, `first`
+    // iterations, evaluation, record and flag download -- as ONE CUDA graph launch: the ~25 driver calls per
+    // registration become one, which is what the host side of a short registration costs.  The graph is
+    // cached per workspace and keyed by everything baked into it.
+    bool graphed = false;
+    if (predict && !prof && !horn && search_config().graphs && first <= D.max_iterations)
+    {
+        const AlignGraphKey key = {ws->d_scratch, ws->h_pinned, (uint64_t)max_points, (uint64_t)total_queries,
+                                   (uint32_t)views.size(), G, first, (uint32_t)matcher_k(D)};
+        cudaGraphExec_t exec = ws->find_align_graph(key);
+        if (!exec && !ws->graph_failed)
+        {
+            cudaGraph_t graph = nullptr;
+            const uint64_t launches_before = ws->launches;
+            bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok)
+            {
+                enqueue_setup();
+                for (uint32_t i = 0; i < first; i++)
+                {
+                    launch_match_search(ctx, ws, max_points, n, d_clouds, d_jobs, d_nn);
+                    launch_fit<false>(ws, D, mgrid, d_clouds, d_jobs, d_nn, d_partials, no_out, d_pairs);
+                    solve_kernel<<<(unsigned)n, kSolveThreads, 0, s>>>(d_clouds, d_jobs, d_partials, G, D, d_active);
+                    ws->launches++;
+                }
+                evaluate();
+                cudaMemcpyAsync(h_flags, d_active, sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
+                ok = cudaStreamEndCapture(s, &graph) == cudaSuccess && graph != nullptr &&
+                     setup_err == cudaSuccess && eval_err == cudaSuccess;
+                if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+                if (graph) cudaGraphDestroy(graph);
+            }
+            const uint64_t per_launch = ws->launches - launches_before;
+            ws->launches = launches_before;  // captured, not launched
+            if (ok)
+                ws->store_align_graph(key, exec, per_launch);
+            else
+            {
+                cudaGetLastError();
+                exec = nullptr;
+                ws->graph_failed = true;  // this workspace keeps to plain launches
+                setup_err = eval_err = cudaSuccess;
+            }
+        }
+        if (exec)
+        {
+            B2_CUDA_TRY(cudaGraphLaunch(exec, s));
+            ws->launches += ws->align_graph_launches(key);
+            {
+                std::lock_guard<std::mutex> lk(ctx->mtx);
+                ctx->prof.graph_replays++;
+            }
+            B2_CUDA_TRY(cudaStreamSynchronize(s));
+            enq = first, batch = 1, graphed = true;
+            finished = (h_flags[0] == 0);
+        }
+    }
+    if (!graphed)
+    {
+        enqueue_setup();
+        B2_CUDA_TRY(setup_err);
+    }
     while (enq < D.max_iterations && !finished)
     {
         const uint32_t want = (batch == 0) ? first : (predict ? 2u : kBatch);

@@ -37,6 +37,7 @@ void Workspace::destroy()
 {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
+    drop_align_graphs();
     if (d_scratch) cudaFree(d_scratch);
     if (h_pinned) cudaFreeHost(h_pinned);
     if (d_flag) cudaFree(d_flag);
@@ -53,6 +54,7 @@ int Workspace::reserve_device(size_t bytes)
 {
     if (bytes <= d_bytes) return B200ICP_OK;
     B2_CUDA_TRY(cudaStreamSynchronize(stream));
+    drop_align_graphs();  // they hold pointers into the old allocation
     if (d_scratch) B2_CUDA_TRY(cudaFree(d_scratch));
     d_scratch = nullptr, d_bytes = 0;
     const size_t want = align_up(bytes + bytes / 4, 1 << 20);
@@ -65,6 +67,7 @@ int Workspace::reserve_pinned(size_t bytes)
 {
     if (bytes <= h_bytes) return B200ICP_OK;
     B2_CUDA_TRY(cudaStreamSynchronize(stream));
+    drop_align_graphs();
     if (h_pinned) B2_CUDA_TRY(cudaFreeHost(h_pinned));
     h_pinned = nullptr, h_bytes = 0;
     const size_t want = align_up(bytes + bytes / 4, 1 << 16);

@@ -49,6 +49,21 @@ struct Carver
     }
 };
 
+// what is baked into a cached CUDA graph of a single registration's first batch
+struct AlignGraphKey
+{
+    void*    d_scratch;
+    void*    h_pinned;
+    uint64_t max_points, total_queries;
+    uint32_t n_views, fit_ctas, first, k;
+    bool operator==(const AlignGraphKey& o) const
+    {
+        return d_scratch == o.d_scratch && h_pinned == o.h_pinned && max_points == o.max_points &&
+               total_queries == o.total_queries && n_views == o.n_views && fit_ctas == o.fit_ctas &&
+               first == o.first && k == o.k;
+    }
+};
+
 struct Workspace
 {
     int          device = 0;
@@ -62,6 +77,41 @@ struct Workspace
     uint64_t     launches = 0;
     uint32_t*    d_flag = nullptr;  // 256 B of device memory / pinned memory for small status words
     uint32_t*    h_flag = nullptr;
+
+    struct AlignGraph
+    {
+        AlignGraphKey   key;
+        cudaGraphExec_t exec;
+        uint64_t        launches;  // kernels one replay launches
+    };
+    std::vector<AlignGraph> align_graphs;
+    bool                    graph_failed = false;
+    cudaGraphExec_t find_align_graph(const AlignGraphKey& k) const
+    {
+        for (const auto& g : align_graphs)
+            if (g.key == k) return g.exec;
+        return nullptr;
+    }
+    uint64_t align_graph_launches(const AlignGraphKey& k) const
+    {
+        for (const auto& g : align_graphs)
+            if (g.key == k) return g.launches;
+        return 0;
+    }
+    void store_align_graph(const AlignGraphKey& k, cudaGraphExec_t e, uint64_t launches)
+    {
+        if (align_graphs.size() >= 8)
+        {  // oldest out
+            cudaGraphExecDestroy(align_graphs.front().exec);
+            align_graphs.erase(align_graphs.begin());
+        }
+        align_graphs.push_back({k, e, launches});
+    }
+    void drop_align_graphs()
+    {
+        for (auto& g : align_graphs) cudaGraphExecDestroy(g.exec);
+        align_graphs.clear();
+    }
 
     int  init(int dev);
     void destroy();

@@ -14,7 +14,7 @@
 // and then every lane walks the shells around its own home cell using shared
 // memory only: an empty layer costs one AND, an empty row one more, a cell
 // one popc.  Candidate coordinates stay in global memory (L1/L2 resident
-// float4, four independent loads in flight).  There is no CTA-wide barrier:
+// float4; eight independent loads in flight on runs of >= 8 points, else four).  There is no CTA-wide barrier:
 // the warps of a CTA work on different items.
 //
 // Results are identical to knn_search<K> (knn_search.cuh), which remains the

@@ -33,6 +33,7 @@ typedef struct b200lo_state
     uint32_t last_icp_iterations, last_icp_termination;
     size_t   last_points_size;
     uint64_t n_graph_edges, n_checked_pairs;
+    uint64_t n_kf_spills, n_kf_reloads; /* key-frame store: clouds spilled to host memory / brought back (process-wide) */
 } b200lo_state_t;
 
 typedef struct b200lo_factor

@@ -146,6 +146,8 @@ int b200icp_cloud_from_device(b200icp_t* icp, const float* dx, const float* dy, 
                               size_t n, float search_radius, b200icp_cloud_t** out);
 void   b200icp_cloud_free(b200icp_cloud_t* c);
 size_t b200icp_cloud_size(const b200icp_cloud_t* c);
+/* bytes of HBM the cloud and its index occupy (key-frame store accounting) */
+size_t b200icp_cloud_device_bytes(const b200icp_cloud_t* c);
 /* original-order coordinates back to the host */
 int b200icp_cloud_download(const b200icp_cloud_t* c, float* x, float* y, float* z);
 

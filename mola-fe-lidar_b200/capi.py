@@ -91,7 +91,7 @@ EXPORTS = [
     "b200icp_last_error", "b200icp_device_count", "b200icp_default_params",
     "b200icp_params_from_yaml", "b200icp_create", "b200icp_create_from_yaml", "b200icp_destroy",
     "b200icp_get_params", "b200icp_device", "b200icp_cloud_upload", "b200icp_cloud_from_device",
-    "b200icp_cloud_free", "b200icp_cloud_size", "b200icp_cloud_download",
+    "b200icp_cloud_free", "b200icp_cloud_size", "b200icp_cloud_device_bytes", "b200icp_cloud_download",
     "b200icp_voxel_decimate", "b200icp_knn", "b200icp_knn_keys_device", "b200icp_merge_keys_device",
     "b200icp_knn_keys_scatter", "b200icp_peer_alloc", "b200icp_peer_free", "b200icp_peer_open",
     "b200icp_peer_close", "b200icp_peer_barrier", "b200icp_knn_keys_exchange", "b200icp_fill_no_key",
@@ -130,6 +130,8 @@ def lib():
     L.b200icp_cloud_free.restype = None
     L.b200icp_cloud_size.argtypes = [vp]
     L.b200icp_cloud_size.restype = C.c_size_t
+    L.b200icp_cloud_device_bytes.argtypes = [vp]
+    L.b200icp_cloud_device_bytes.restype = C.c_size_t
     L.b200icp_cloud_download.argtypes = [vp, fp, fp, fp]
     L.b200icp_voxel_decimate.argtypes = [vp, vp, C.c_float, C.c_int, C.c_float, C.POINTER(vp), up]
     L.b200icp_knn.argtypes = [vp, vp, vp, dp, C.c_uint32, C.c_float, up, fp]

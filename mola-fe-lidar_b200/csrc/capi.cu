@@ -207,6 +207,7 @@ extern "C" void b200icp_cloud_free(b200icp_cloud_t* c)
 }
 
 extern "C" size_t b200icp_cloud_size(const b200icp_cloud_t* c) { return c ? c->n : 0; }
+extern "C" size_t b200icp_cloud_device_bytes(const b200icp_cloud_t* c) { return c ? c->slab_bytes : 0; }
 
 extern "C" int b200icp_cloud_download(const b200icp_cloud_t* c, float* x, float* y, float* z)
 {

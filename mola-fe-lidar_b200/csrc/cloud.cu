@@ -280,6 +280,7 @@ int cloud_alloc(::b200icp* ctx, Workspace* ws, size_t n, float search_radius, b2
         delete c;
         return e == cudaErrorMemoryAllocation ? B200ICP_ERR_NOMEM : B200ICP_ERR_CUDA;
     }
+    c->slab_bytes = cv.off;
     Carver real(c->slab);
     layout(real);
     e = cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming);

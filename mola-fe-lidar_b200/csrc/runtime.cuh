@@ -154,6 +154,7 @@ struct b200icp_cloud
     b200icp* ctx = nullptr;
     size_t   n = 0;
     void*    slab = nullptr;  // one allocation holding everything below
+    size_t   slab_bytes = 0;
     float *  dx = nullptr, *dy = nullptr, *dz = nullptr;
     float4*  pts = nullptr;
     uint32_t* rank = nullptr;

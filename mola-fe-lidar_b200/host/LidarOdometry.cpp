@@ -130,6 +130,7 @@ void LidarOdometry::initialize(const Yaml& c)
     // additive keys of this implementation
     cfg.load_opt("b200_device", params_.device);
     cfg.load_opt("b200_extra_edge_checks", params_.extra_edge_checks);
+    cfg.load_opt("b200_kf_store_budget_mb", params_.kf_store_budget_mb);
     {
         unsigned int seed = (unsigned int)params_.montecarlo_seed;
         cfg.load_opt("b200_montecarlo_seed", seed);
@@ -221,7 +222,7 @@ DeviceCloud::Ptr LidarOdometry::make_cloud(const CObservation& o)
         check_rc(b200icp_cloud_upload(ctx, o.xs(), o.ys(), o.zs(), o.size(), cloud_search_radius_, &raw),
                  "b200icp_cloud_upload");
     }
-    auto              raw_ptr = std::make_shared<DeviceCloud>(raw);
+    auto              raw_ptr = std::make_shared<DeviceCloud>(raw, ctx, cloud_search_radius_);
     ProfilerEntry     tle1(profiler_, "doProcessNewObservation.1.filter_pointclouds");
     if (params_.voxel_decimation_resolution > 0)
     {
@@ -229,7 +230,7 @@ DeviceCloud::Ptr LidarOdometry::make_cloud(const CObservation& o)
         check_rc(b200icp_voxel_decimate(ctx, raw, (float)params_.voxel_decimation_resolution,
                                         params_.voxel_use_average ? 1 : 0, cloud_search_radius_, &dec, nullptr),
                  "b200icp_voxel_decimate");
-        return std::make_shared<DeviceCloud>(dec);
+        return std::make_shared<DeviceCloud>(dec, ctx, cloud_search_radius_);
     }
     return raw_ptr;
 }
@@ -339,6 +340,7 @@ void LidarOdometry::doProcessNewObservation(CObservation::Ptr& o)
                 worldmodel_->entity_annotations_by_id(new_kf_id).emplace(ANNOTATION_NAME_PC_LAYERS, this_obs_points);
                 worldmodel_->entities_unlock_for_write();
             }
+            kf_store_add(this_obs_points);
             // 2) New SE(3) constraint between consecutive Keyframes (cpp:432-470)
             if (state_.last_kf != INVALID_ID)
             {
@@ -544,12 +546,15 @@ void LidarOdometry::doCheckForNonAdjacentKFs(ICP_Input::Ptr d)
                 guesses[6 * i + 4] = original_guess.pitch;
                 guesses[6 * i + 5] = original_guess.roll;
             }
-            std::vector<const b200icp_cloud_t*> fr(N, d->from_pc->h), to(N, d->to_pc->h);
+            CloudPin pin_from(d->from_pc), pin_to(d->to_pc);  // resident (re-uploaded if spilled) for the batch
+            if (!pin_from.h || !pin_to.h) throw std::runtime_error(std::string("cloud reload: ") + b200icp_last_error());
+            std::vector<const b200icp_cloud_t*> fr(N, pin_from.h), to(N, pin_to.h);
             std::vector<b200icp_result_t>       res(N);
             check_rc(b200icp_align_batch(params_.icp.at(d->align_kind).icp, N, fr.data(), to.data(),
                                          guesses.data(), res.data()),
                      "b200icp_align_batch");
             state_.n_icp += N;
+            kf_store_enforce_budget();
             for (size_t i = 0; i < N; i++)
             {
                 if (res[i].quality > icp_out.goodness)
@@ -598,6 +603,45 @@ void LidarOdometry::doCheckForNonAdjacentKFs(ICP_Input::Ptr d)
     }
 }
 
+// ---- key-frame cloud store ---------------------------------------------------
+void LidarOdometry::kf_store_add(const DeviceCloud::Ptr& c)
+{
+    {
+        std::lock_guard<std::mutex> lk(kf_store_mtx_);
+        kf_store_.push_back(c);
+    }
+    kf_store_enforce_budget();
+}
+
+void LidarOdometry::kf_store_enforce_budget()
+{
+    if (!(params_.kf_store_budget_mb > 0)) return;
+    const double                  budget = params_.kf_store_budget_mb * 1024.0 * 1024.0;
+    std::lock_guard<std::mutex>   lk(kf_store_mtx_);
+    std::vector<DeviceCloud::Ptr> alive;
+    for (auto it = kf_store_.begin(); it != kf_store_.end();)
+    {
+        if (auto p = it->lock())
+        {
+            alive.push_back(std::move(p));
+            ++it;
+        }
+        else
+            it = kf_store_.erase(it);
+    }
+    double total = 0;
+    for (const auto& c : alive) total += (double)c->device_bytes();
+    // least recently used first (a cloud is "used" when it is created and whenever a registration pins it)
+    std::sort(alive.begin(), alive.end(),
+              [](const DeviceCloud::Ptr& a, const DeviceCloud::Ptr& b) { return a->last_use() < b->last_use(); });
+    for (const auto& c : alive)
+    {
+        if (total <= budget) break;
+        const double bytes = (double)c->device_bytes();
+        if (bytes > 0 && c->spill()) total -= bytes;
+    }
+}
+
 // cpp:851-895
 void LidarOdometry::run_one_icp(const ICP_Input& in, ICP_Output& out)
 {
@@ -618,9 +662,15 @@ void LidarOdometry::run_one_icp(const ICP_Input& in, ICP_Output& out)
         check_rc(b200icp_create(&in.icp_params, params_.device, &tmp), "b200icp_create");
         icp = tmp;
     }
-    const int rc = b200icp_align(icp, in.from_pc->h, in.to_pc->h, guess, &icp_result);
+    int rc;
+    {
+        CloudPin pin_from(in.from_pc), pin_to(in.to_pc);  // resident (re-uploaded if spilled) for the call
+        if (!pin_from.h || !pin_to.h) throw std::runtime_error(std::string("cloud reload: ") + b200icp_last_error());
+        rc = b200icp_align(icp, pin_from.h, pin_to.h, guess, &icp_result);
+    }
     if (tmp) b200icp_destroy(tmp);
     check_rc(rc, "b200icp_align");
+    kf_store_enforce_budget();  // a reload may have pushed the store over its budget
     state_.n_icp++;
 
     if (icp_result.quality > 0)

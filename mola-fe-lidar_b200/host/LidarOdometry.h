@@ -128,6 +128,9 @@ class LidarOdometry : public FrontEndBase
          *  (cpp:493-508), so that every processed scan costs exactly one
          *  consecutive-scan registration (the unit bench.py times) */
         bool extra_edge_checks{true};
+        /** additive key `b200_kf_store_budget_mb`: HBM the key-frame clouds may hold together; beyond it the
+         *  least recently used ones are spilled to host memory (0 = no limit, the default) */
+        double kf_store_budget_mb{0.0};
     };
     Parameters params_;
 
@@ -198,6 +201,13 @@ class LidarOdometry : public FrontEndBase
     void checkForNearbyKFs();
     void release_icp_objects();
     DeviceCloud::Ptr make_cloud(const CObservation& o);
+
+    /** Key-frame cloud store: the clouds the world model holds (cpp:384-388) stay in HBM up
+     *  to `kf_store_budget_mb`; beyond it the least recently used, unpinned ones are spilled to host memory. */
+    void kf_store_add(const DeviceCloud::Ptr& c);
+    void kf_store_enforce_budget();
+    std::mutex                                 kf_store_mtx_;
+    std::vector<std::weak_ptr<DeviceCloud>>    kf_store_;
 
     std::mutex local_pose_graph_mtx;
     float      cloud_search_radius_{0.f};

@@ -170,6 +170,8 @@ extern "C" int b200lo_get_state(b200lo_t* lo, b200lo_state_t* out)
     out->last_points_size = s.last_points ? s.last_points->size() : 0;
     out->n_graph_edges = s.local_pose_graph.graph.edges.size();
     out->n_checked_pairs = s.local_pose_graph.checked_KF_pairs.size();
+    out->n_kf_spills = DeviceCloud::spills().load();
+    out->n_kf_reloads = DeviceCloud::reloads().load();
     return 0;
 }
 

@@ -7,6 +7,7 @@
 // 484-490), WorldModel annotations + neighbours + RW locks (cpp:377-428,
 // 614-669).  A real MOLA build replaces this header with <mola-kernel/...>.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <functional>
 #include <future>
@@ -59,17 +60,114 @@ struct CObservation
     const float* zs() const { return pz ? pz : z.data(); }
 };
 
-/** One point layer of mp2p_icp::metric_map_t, resident on the device. */
+/** One point layer of mp2p_icp::metric_map_t, resident on the device.
+ *
+ *  Key-frame clouds outlive the scan that produced them (they sit in the world
+ *  model, LidarOdometry.cpp:384-388, and are fetched again for extra edges,
+ *  cpp:658-666).  So that a long session does not run out of HBM, a cloud can be
+ *  SPILLED: its coordinates are downloaded to host memory and the device copy
+ *  (points + search index) is freed; pin() brings it back -- same points, same
+ *  index, same registration results -- and keeps it resident until unpin(). */
 struct DeviceCloud
 {
     using Ptr = std::shared_ptr<DeviceCloud>;
-    b200icp_cloud_t* h = nullptr;
-    explicit DeviceCloud(b200icp_cloud_t* c) : h(c) {}
+    b200icp_cloud_t* h = nullptr;  // null while spilled
+    explicit DeviceCloud(b200icp_cloud_t* c, b200icp_t* owner = nullptr, float search_radius = 0.f)
+        : h(c), owner_(owner), radius_(search_radius), n_(b200icp_cloud_size(c))
+    {
+        last_use_ = ++clock();  // a new cloud is the most recently used one
+    }
     DeviceCloud(const DeviceCloud&) = delete;
     DeviceCloud& operator=(const DeviceCloud&) = delete;
     ~DeviceCloud() { b200icp_cloud_free(h); }
-    size_t size() const { return b200icp_cloud_size(h); }
-    bool   empty() const { return size() == 0; }
+    size_t size() const { return n_; }
+    bool   empty() const { return n_ == 0; }
+
+    /** HBM held right now (0 while spilled) */
+    size_t device_bytes() const
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        return h ? b200icp_cloud_device_bytes(h) : 0;
+    }
+    bool resident() const
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        return h != nullptr;
+    }
+    uint64_t last_use() const { return last_use_.load(); }
+    /** handle for a registration: re-uploads a spilled cloud; nullptr on failure */
+    b200icp_cloud_t* pin()
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        if (!h && owner_)
+        {
+            b200icp_cloud_t* c = nullptr;
+            if (b200icp_cloud_upload(owner_, sx_.data(), sy_.data(), sz_.data(), n_, radius_, &c) != B200ICP_OK)
+                return nullptr;
+            h = c;
+            sx_ = std::vector<float>(), sy_ = std::vector<float>(), sz_ = std::vector<float>();
+            reloads()++;
+        }
+        pins_++;
+        last_use_ = ++clock();
+        return h;
+    }
+    void unpin()
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        if (pins_ > 0) pins_--;
+    }
+    /** frees the device copy if nobody is using it; false when pinned, spilled already or not spillable */
+    bool spill()
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        if (!h || pins_ > 0 || !owner_) return false;
+        std::vector<float> x(n_), y(n_), z(n_);
+        if (n_ && b200icp_cloud_download(h, x.data(), y.data(), z.data()) != B200ICP_OK) return false;
+        b200icp_cloud_free(h);
+        h = nullptr;
+        sx_.swap(x), sy_.swap(y), sz_.swap(z);
+        spills()++;
+        return true;
+    }
+    static std::atomic<uint64_t>& spills()
+    {
+        static std::atomic<uint64_t> v{0};
+        return v;
+    }
+    static std::atomic<uint64_t>& reloads()
+    {
+        static std::atomic<uint64_t> v{0};
+        return v;
+    }
+
+   private:
+    static std::atomic<uint64_t>& clock()
+    {
+        static std::atomic<uint64_t> v{0};
+        return v;
+    }
+    mutable std::mutex    m_;
+    b200icp_t*            owner_ = nullptr;
+    float                 radius_ = 0.f;
+    size_t                n_ = 0;
+    int                   pins_ = 0;
+    std::atomic<uint64_t> last_use_{0};
+    std::vector<float>    sx_, sy_, sz_;  // coordinates while spilled
+};
+
+/** RAII use of a cloud by one registration */
+struct CloudPin
+{
+    DeviceCloud::Ptr c;
+    b200icp_cloud_t* h = nullptr;
+    explicit CloudPin(DeviceCloud::Ptr cloud) : c(std::move(cloud)), h(c ? c->pin() : nullptr) {}
+    CloudPin(const CloudPin&) = delete;
+    CloudPin& operator=(const CloudPin&) = delete;
+    ~CloudPin()
+    {
+        if (c) c->unpin();
+    }
 };
 
 struct FactorRelativePose3

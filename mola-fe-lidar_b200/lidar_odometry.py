@@ -35,6 +35,7 @@ class State(C.Structure):
         ("last_icp_iterations", C.c_uint32), ("last_icp_termination", C.c_uint32),
         ("last_points_size", C.c_size_t),
         ("n_graph_edges", C.c_uint64), ("n_checked_pairs", C.c_uint64),
+        ("n_kf_spills", C.c_uint64), ("n_kf_reloads", C.c_uint64),
     ]
 
 

@@ -36,6 +36,16 @@ int b200icp_cloud_upload(b200icp_t* icp, const float* x, const float* y, const f
 }
 void   b200icp_cloud_free(b200icp_cloud_t* c) { free(c); }
 size_t b200icp_cloud_size(const b200icp_cloud_t* c) { return c ? c->n : 0; }
+size_t b200icp_cloud_device_bytes(const b200icp_cloud_t* c) { return c ? 100 * c->n : 0; }
+static unsigned long g_downloads = 0;
+unsigned long        fake_download_calls(void) { return g_downloads; }
+int b200icp_cloud_download(const b200icp_cloud_t* c, float* x, float* y, float* z)
+{
+    if (!c || !x || !y || !z) return -1;
+    g_downloads++;
+    for (size_t i = 0; i < c->n; i++) x[i] = c->p0[0], y[i] = c->p0[1], z[i] = c->p0[2];
+    return 0;
+}
 int b200icp_voxel_decimate(b200icp_t* icp, const b200icp_cloud_t* in, float resolution, int use_average,
                            float search_radius, b200icp_cloud_t** out, uint32_t* keep_idx)
 {

@@ -154,3 +154,35 @@ def test_extra_edges_between_nearby_keyframes(oracle, tmp_path):
     assert len(extra) >= 1, "expected at least one non-adjacent KF edge"
     assert st["n_factors"] == len(f) and st["n_localizations"] == 14
     lo.close()
+
+
+def test_keyframe_store_budget_gives_identical_factors(tmp_path):
+    """Key-frame cloud store: with `b200_kf_store_budget_mb`
+    small enough for about two clouds, older key-frame clouds are spilled to
+    host memory and re-uploaded (index rebuilt) when an extra-edge registration
+    needs them -- every factor must equal the unlimited run bit for bit."""
+    from mola_fe_lidar_b200 import lidar_odometry as lom
+    scans, poses = _sequence(14, n_pts=20000)
+    txt = open(os.path.join(lom.PARAMS_DIR, "kitti-default.yaml")).read()
+    prm = tmp_path / "kitti-lowgood.yaml"
+    prm.write_text(txt.replace("min_icp_goodness: 0.50", "min_icp_goodness: 0.05"))
+
+    def run(extra):
+        lo = lom.LidarOdometry(yaml_text=lom.system_yaml(params_file=str(prm), extra=extra))
+        s0 = lo.state()
+        for i, s in enumerate(scans):
+            lo.onNewObservation(s, 0.1 * i, sync=True)
+            lo.wait_idle()  # extra-edge jobs in a fixed order: factor lists comparable
+        lo.wait_idle()
+        st, f = lo.state(), lo.factors()
+        lo.close()
+        return st, f, int(st["n_kf_spills"] - s0["n_kf_spills"]), int(st["n_kf_reloads"] - s0["n_kf_reloads"])
+
+    st_a, f_a, sp_a, rl_a = run("")
+    st_b, f_b, sp_b, rl_b = run("  b200_kf_store_budget_mb: 4\n")  # a 20k-point cloud with its index is ~1.8 MB
+    assert sp_a == 0 and rl_a == 0
+    assert sp_b >= 1 and rl_b >= 1, (sp_b, rl_b)
+    assert st_a["n_keyframes"] == st_b["n_keyframes"] >= 3 and st_a["n_checked_pairs"] == st_b["n_checked_pairs"] >= 1
+    assert len(f_a) == len(f_b)
+    for (a0, a1, pa), (b0, b1, pb) in zip(sorted(f_a, key=lambda x: (x[0], x[1])), sorted(f_b, key=lambda x: (x[0], x[1]))):
+        assert (a0, a1) == (b0, b1) and np.array_equal(pa, pb)

@@ -180,3 +180,35 @@ def test_additive_key_disables_extra_edge_checks(fake_lib):
     assert off["n_icp"] == off["n_processed"] - 1  # exactly one registration per scan after the first
     assert "doProcessNewObservation.6.checkForNearbyKFs" not in off["profile"]
     assert "doProcessNewObservation.0.upload_and_index" in off["profile"]
+
+
+def test_keyframe_store_spills_and_reloads_without_changing_results(fake_lib):
+    """Key-frame cloud store: with a budget (additive key
+    b200_kf_store_budget_mb) the least recently used key-frame clouds are
+    spilled to host memory and re-uploaded when an extra-edge registration needs
+    them; key-frames, factors and poses are those of the unlimited run."""
+    body = """
+        fake.fake_download_calls.restype = ctypes.c_ulong
+        lo = lom.LidarOdometry(yaml_text=lom.system_yaml(extra=%r))
+        k = 0
+        for i in range(31):
+            lo.onNewObservation(scan(2.0 * i, n=1000), 0.1 * k); k += 1; lo.wait_idle()
+        for i in range(30, -1, -1):
+            lo.onNewObservation(scan(2.0 * i, y=6.0, n=1000), 0.1 * k); k += 1; lo.wait_idle()
+        lo.wait_idle()
+        s = lo.state()
+        out["n_keyframes"] = int(s["n_keyframes"]); out["n_factors"] = int(s["n_factors"])
+        out["n_checked_pairs"] = int(s["n_checked_pairs"]); out["n_icp"] = int(s["n_icp"])
+        out["spills"] = int(s["n_kf_spills"]); out["reloads"] = int(s["n_kf_reloads"])
+        out["downloads"] = int(fake.fake_download_calls())
+        out["factors"] = sorted((int(a), int(b), [round(float(v), 9) for v in p]) for a, b, p in lo.factors())
+        lo.close()
+    """
+    # the test double charges 100 bytes per point: 1000-point clouds = 100 kB each, budget = 3 clouds
+    free = run_child(fake_lib, body % "")
+    tight = run_child(fake_lib, body % "  b200_kf_store_budget_mb: 0.3\n")
+    assert free["spills"] == 0 and free["reloads"] == 0 and free["downloads"] == 0
+    assert tight["spills"] >= free["n_keyframes"] - 4 and tight["downloads"] == tight["spills"]
+    assert tight["reloads"] >= 1  # the return leg registers against spilled key-frames of the outbound leg
+    for key in ("n_keyframes", "n_factors", "n_checked_pairs", "n_icp", "factors"):
+        assert tight[key] == free[key], key

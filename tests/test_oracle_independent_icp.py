@@ -158,3 +158,80 @@ def test_oracle_agrees_with_independent_numpy_icp(oracle, seed, guess):
     assert np.abs(ro["t"] - T[:3, 3]).max() < 1e-7
     assert np.abs(ro["R"] - T[:3, :3]).max() < 1e-7
     assert np.abs(ro["pose"][:3] - truth[:3]).max() < 5e-3   # and both are right
+
+
+# ---------------------------------------------------------------------------
+# rows M, N: Matcher_Points_DistanceThreshold + Solver_Horn with the scale-outlier
+# rule, restated independently (the rotation comes from an SVD / Kabsch solve
+# instead of Horn's quaternion eigenvector: the same optimum by a different road)
+def _match_points(tree, G32, L32, R, t, thr):
+    q = (L32.astype(np.float64) @ R.T + t).astype(np.float32)
+    thr2 = np.float32(thr) * np.float32(thr)
+    nb = _knn_f32(tree, G32, q, 1, thr2)
+    idx = [i for i, lst in enumerate(nb) if lst and lst[0][0] < thr2]        # strict (A.8 / orc_match_points)
+    nn = [nb[i][0][1] for i in idx]
+    return np.array(idx, dtype=int), np.array(nn, dtype=int)
+
+
+def _horn_kabsch(P, Q, scale_thr=1.1):
+    """A.10: centroids over ALL pairs; a pair whose centroid-relative norms
+    differ by more than the threshold ratio is left out of the rotation."""
+    pc, qc = P.mean(axis=0), Q.mean(axis=0)
+    b, a = P - pc, Q - qc
+    bn, an = np.linalg.norm(b, axis=1), np.linalg.norm(a, axis=1)
+    mx, mn = np.maximum(bn, an), np.minimum(bn, an)
+    keep = (mn > 0) & (mx / np.where(mn > 0, mn, 1.0) <= scale_thr)
+    if keep.sum() < 3:
+        return None
+    S = b[keep].T @ a[keep]                                      # sum b a^T
+    U, _, Vt = np.linalg.svd(S)
+    D = np.diag([1.0, 1.0, np.sign(np.linalg.det(Vt.T @ U.T))])
+    R = Vt.T @ D @ U.T
+    T = np.eye(4)
+    T[:3, :3], T[:3, 3] = R, qc - R @ pc
+    return T
+
+
+def independent_icp_p2p_horn(G32, L32, guess, thr, max_it, step_t=5e-5, step_r=1e-5, q_thr=0.10):
+    tree = cKDTree(G32.astype(np.float64))
+    T = np.eye(4)
+    T[:3, :3] = _rot_ypr(*guess[3:])
+    T[:3, 3] = guess[:3]
+    it, reason = 0, 3
+    while it < max_it:
+        idx, nn = _match_points(tree, G32, L32, T[:3, :3], T[:3, 3], thr)
+        if len(idx) == 0:
+            reason = 1
+            break
+        Tn = _horn_kabsch(L32[idx].astype(np.float64), G32[nn].astype(np.float64))
+        if Tn is None:
+            reason = 2
+            break
+        d = _se3_log(np.linalg.inv(T) @ Tn)
+        T = Tn
+        if np.linalg.norm(d[:3]) < step_t and np.linalg.norm(d[3:]) < step_r:
+            reason = 4
+            break
+        it += 1
+    q = (L32.astype(np.float64) @ T[:3, :3].T + T[:3, 3]).astype(np.float32)
+    q2 = np.float32(q_thr) * np.float32(q_thr)
+    hits = sum(1 for lst in _knn_f32(tree, G32, q, 1, q2) if lst and lst[0][0] < q2)
+    return T, it, reason, hits / len(L32)
+
+
+def test_oracle_p2p_horn_agrees_with_independent_kabsch_icp(oracle):
+    rng = np.random.default_rng(5)
+    G = _scene(rng, 2200)
+    truth = np.array([0.10, 0.06, -0.02, np.deg2rad(0.6), np.deg2rad(-0.2), np.deg2rad(0.1)])
+    Rt, tt = _rot_ypr(*truth[3:]), truth[:3]
+    sel = rng.choice(len(G), size=1500, replace=False)
+    L = ((G[sel].astype(np.float64) - tt) @ Rt + rng.normal(0, 0.004, size=(1500, 3))).astype(np.float32)
+    prm = oracle.default_params(max_iterations=8, solver_kind=1, matcher_kind=1, distance_threshold=0.5)
+    ro = oracle.icp_align(oracle.Cloud(G), oracle.Cloud(L), np.zeros(6), prm, kdtree=True)
+    T, it, reason, quality = independent_icp_p2p_horn(G, L, np.zeros(6), 0.5, 8)
+    assert ro["termination_reason"] == reason and reason in (3, 4)
+    assert ro["n_iterations"] == it
+    assert ro["quality"] == pytest.approx(quality, abs=1e-12)
+    assert np.abs(ro["t"] - T[:3, 3]).max() < 1e-7
+    assert np.abs(ro["R"] - T[:3, :3]).max() < 1e-7
+    assert np.abs(ro["pose"][:3] - truth[:3]).max() < 2e-2

@@ -169,7 +169,13 @@ class PeerExchange:
             dist.all_gather_object(handles, handle)  # also orders the zeroing before any remote access
         else:
             handles[0] = handle
-        self.bases = [self.base if r == rank else icp.peer_open(handles[r]) for r in range(world)]
+        self.bases = []
+        try:
+            for r in range(world):
+                self.bases.append(self.base if r == rank else icp.peer_open(handles[r]))
+        except Exception:
+            self.close()  # unmap what was mapped, free the local buffer
+            raise
         self.ptrs = [b + self.HEADER for b in self.bases]
         self.local = self.ptrs[rank]
         self.epoch = 0
@@ -180,11 +186,11 @@ class PeerExchange:
         self.icp.peer_barrier(self.bases, self.rank, self.epoch)
 
     def close(self):
-        for r, p in enumerate(self.bases):
+        for r, p in enumerate(getattr(self, "bases", [])):
             if r != self.rank and p:
                 self.icp.peer_close(p)
         self.bases, self.ptrs = [], []
-        if self.base:
+        if getattr(self, "base", None):
             self.icp.peer_free(self.base)
             self.base = self.local = None
 
@@ -217,9 +223,11 @@ class ShardedMap:
         per = (nq + self.world - 1) // self.world
         need = max(8, 2 * self.world * per * k * 8)  # gather region + result region (see b200icp_knn_keys_exchange)
         if self.peers is None or self.peers.nbytes < need:
+            # no collective here: nobody touches a rank's buffer after the last barrier of a query, and a
+            # rank whose exchange could not be set up must not leave the others waiting in one
             if self.peers is not None:
-                self._barrier()
                 self.peers.close()
+                self.peers = None
             self.peers = PeerExchange(s.icp, self.rank, self.world, self.dist, need)
         px = self.peers
         out = torch.empty((nq, k), dtype=torch.int64, device=s.device)
@@ -232,8 +240,7 @@ class ShardedMap:
         return out
 
     def close(self):
-        if self.peers is not None:
-            self._barrier()
+        if self.peers is not None:  # safe without a collective: every query ends with a barrier
             self.peers.close()
             self.peers = None
 

@@ -212,3 +212,19 @@ def test_keyframe_store_spills_and_reloads_without_changing_results(fake_lib):
     assert tight["reloads"] >= 1  # the return leg registers against spilled key-frames of the outbound leg
     for key in ("n_keyframes", "n_factors", "n_checked_pairs", "n_icp", "factors"):
         assert tight[key] == free[key], key
+
+
+def test_cpp_example_builds_and_runs_against_the_test_double(fake_lib, tmp_path):
+    """examples/odometry_cpp.cpp: the module driven from C++ (initialize(Yaml) +
+    onNewObservation, as mola-launcher drives the reference) links against the
+    two shared libraries and runs end to end with the device test double."""
+    exe = str(tmp_path / "odometry_cpp")
+    lib_dir = os.path.join(ROOT, "mola-fe-lidar_b200", "lib")
+    subprocess.check_call(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-std=c++17", "-O1",
+                           "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "mola-fe-lidar_b200", "host"),
+                           os.path.join(ROOT, "examples", "odometry_cpp.cpp"), "-L", lib_dir,
+                           "-lmola_fe_lidar_b200", "-lb200icp", f"-Wl,-rpath,{lib_dir}", "-lpthread", "-o", exe])
+    p = subprocess.run([exe, os.path.join(ROOT, "mola-fe-lidar_b200")], env=dict(os.environ, LD_PRELOAD=fake_lib),
+                       capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert "scan 7: processed 8, registrations" in p.stdout and "factors:" in p.stdout

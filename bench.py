@@ -243,6 +243,30 @@ def knn_microbench(torch, icp, scans, poses, dev, peak):
         out.append({"case": name, "n_queries": nq, "n_ref": len(ref) if ref else len(cl[0]), "k": k,
                     "radius_m": 0.7, "kernel_ms": ms, "queries_per_s": qps,
                     "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak})
+    # the same kernel on points uniform in a box (SURVEY 8d asks for both distributions): 120k x 120k in
+    # 60 x 60 x 6 m, about 8 points within the 0.7 m radius of a query
+    try:
+        rngu = np.random.default_rng(3)
+        box = np.float32([60.0, 60.0, 6.0])
+        ua = icp.upload((rngu.random((120000, 3), dtype=np.float32) * box))
+        ub = icp.upload((rngu.random((120000, 3), dtype=np.float32) * box))
+        for k in (1, 6):
+            keys = torch.empty((120000, k), dtype=torch.int64, device=dev)
+            for w in range(2):
+                icp.knn_keys_device(ua, ub, k, 0.7, keys.data_ptr())
+            icp.profile_reset()
+            for r in range(6):
+                icp.knn_keys_device(ua, ub, k, 0.7, keys.data_ptr())
+            pr = icp.profile()
+            ms = pr["knn_ms"] / max(pr["knn_launches"], 1)
+            qps = 120000 / (ms * 1e-3)
+            gbs = qps * KNN_ALGO_BYTES[k] / 1e9
+            out.append({"case": "uniform_box_120k_vs_120k", "n_queries": 120000, "n_ref": 120000, "k": k,
+                        "radius_m": 0.7, "kernel_ms": ms, "queries_per_s": qps, "algorithmic_GBps": gbs,
+                        "frac_of_hbm_peak": gbs / peak})
+        ua.free(), ub.free()
+    except Exception as e:
+        out.append({"case": "uniform_box_120k_vs_120k", "error": f"{type(e).__name__}: {e}"[:200]})
     icp.profile_enable(False)
     # config C3's shape: scan-to-map registration, raw 120k-pt scans (sensor frame) against the merged map
     from mola_fe_lidar_b200 import scene
@@ -565,17 +589,27 @@ def run_b200(args, rank, world, local_rank):
     peak, peak_src = load_peaks()
     extras = {}
     if not args.no_extras:
-        try:
-            if rank == 0:
-                extras["knn"], extras["scan_to_map"] = knn_microbench(torch, icp, scans, poses, dev, peak)
-            shared_scans, shared_poses = (scans, poses) if world == 1 else make_scans(1)
-            extras["batch_lc"] = batch_lc(torch, dist, capi, lidar_odometry, shared_scans, rank, world, local_rank,
-                                          dev, args.pairs_per_gpu)
-            extras["sharded_knn"] = sharded_knn(torch, dist, capi, shared_scans, shared_poses, rank, world,
-                                                local_rank, dev, args.map_points_per_gpu)
-        except Exception as e:  # the contract line must still be printed
-            extras["extras_error"] = f"{type(e).__name__}: {e}"
-            log("[bench] extras failed:", extras["extras_error"])
+        def section(name, fn):
+            try:
+                return fn()
+            except Exception as e:  # the contract line must still be printed, the other sections still run
+                extras.setdefault("extras_error", {})[name] = f"{type(e).__name__}: {e}"[:300]
+                log(f"[bench] section {name} failed:", extras["extras_error"][name])
+                return None
+
+        if rank == 0:
+            r = section("knn", lambda: knn_microbench(torch, icp, scans, poses, dev, peak))
+            if r is not None:
+                extras["knn"], extras["scan_to_map"] = r
+        shared_scans, shared_poses = (scans, poses) if world == 1 else make_scans(1)
+        r = section("batch_lc", lambda: batch_lc(torch, dist, capi, lidar_odometry, shared_scans, rank, world,
+                                                 local_rank, dev, args.pairs_per_gpu))
+        if r is not None:
+            extras["batch_lc"] = r
+        r = section("sharded_knn", lambda: sharded_knn(torch, dist, capi, shared_scans, shared_poses, rank, world,
+                                                       local_rank, dev, args.map_points_per_gpu))
+        if r is not None:
+            extras["sharded_knn"] = r
 
     if rank == 0:
         launches = max(prof["match_launches"], 1)

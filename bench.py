@@ -131,6 +131,29 @@ class ClockSampler:
                 "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
+def next_guess(step, pose):
+    """Constant-velocity initial guess for step+1 from the result of `step`
+    with equal time steps: x, y, z, yaw only (LidarOdometry.cpp:272-275,
+    305-308); identity when the back-and-forth walk over the scans turns round."""
+    back = scan_index(step + 2) < scan_index(step + 1)
+    was_back = scan_index(step + 1) < scan_index(step)
+    if back != was_back:
+        return np.zeros(6)
+    return np.array([pose[0], pose[1], pose[2], pose[3], 0.0, 0.0])
+
+
+def workload_config(n_pts):
+    """The SAME dict in both arms (`--impl b200` and `--impl reference`)."""
+    return {"workload": "c2_kitti64_120k_scan_to_scan_odometry", "points_per_scan": int(n_pts),
+            "icp_settings": "icp-settings-regular.yaml via kitti-default.yaml",
+            "guess": "constant-velocity from the previous registration of the same sequence "
+                     "(LidarOdometry.cpp:272-275); the first registration of a sequence (identity guess) is warm-up",
+            "sequence": "synthetic 64-beam, 1.0 m / 0.29 deg per scan, seed 1 + rank; forward-only when "
+                        "warmup + steps + 3 <= 48 scans, else walked back and forth",
+            "l2": "inputs (2 x 1.9 MB float4 + index) are L2-resident by nature; each step "
+                  "registers a different scan pair, no flush"}
+
+
 def make_scans(seed):
     from mola_fe_lidar_b200 import scene
     t = time.time()
@@ -141,7 +164,10 @@ def make_scans(seed):
 
 # --------------------------------------------------------------------- reference arm
 def run_reference(args, rank):
-    """CPU oracle port on all host threads; each step = one registration per thread."""
+    """CPU oracle port on all host threads.  Every thread walks the SAME kind of
+    sequence as the GPU arm -- consecutive scan pairs, each registration started
+    from the constant-velocity guess of its own previous result -- staggered by
+    one scan per thread; a step = one registration per thread."""
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -153,38 +179,41 @@ def run_reference(args, rank):
     prm = O.default_params()
     for c in clouds:  # kd-trees are built lazily on first query (as in MRPT): warm them once
         O.knn(c, scans[0][:8], 1, 0.49, kdtree=True)
+    guesses = [np.zeros(6) for _ in range(threads)]
+    iters = []
 
-    def one_step(step):
-        res = [None] * threads
-
+    def one_step(step, record):
         def work(t):
-            i = scan_index(step * threads + t)
-            j = scan_index(step * threads + t + 1)
-            res[t] = O.icp_align(clouds[i], clouds[j], np.zeros(6), prm, kdtree=True)
+            s_t = step + t  # this thread's position in its own walk over the scans
+            r = O.icp_align(clouds[scan_index(s_t)], clouds[scan_index(s_t + 1)], guesses[t], prm, kdtree=True)
+            guesses[t] = next_guess(s_t, r["pose"])
+            if record:
+                iters.append(r["n_iterations"] + 1)
         th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
         [x.start() for x in th]
         [x.join() for x in th]
-        return res
 
-    for w in range(args.warmup):
-        one_step(w)
+    warm = max(args.warmup, 1)  # the first registration of every thread has no velocity guess yet
+    for w in range(warm):
+        one_step(w, False)
     t0 = time.time()
     for s in range(args.steps):
-        one_step(args.warmup + s)
+        one_step(warm + s, True)
     dt = time.time() - t0
     regs = args.steps * threads
     value = regs / dt
     out = {
         "impl": "reference", "metric": "icp_registrations_per_sec", "value": value,
-        "unit": "registrations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "unit": "registrations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 search / f64 solve", "data": "synthetic",
-        "config": {"workload": "c2_kitti64_120k_scan_to_scan_odometry", "points_per_scan": 120000,
-                   "icp_settings": "icp-settings-regular.yaml", "timing": "host clock, CPU only"},
+        "config": workload_config(len(scans[0])),
+        "mean_outer_iterations": float(np.mean(iters)) if iters else None,
+        "timing": "host clock, CPU only",
         "cpu_baseline": {"value": value, "unit": "registrations/s", "cores": threads, "kind": "port",
-                         "sample": f"{regs} registrations of consecutive 120k-pt scans, one per thread per step "
-                                   f"(oracle/icp_oracle.c, kd-tree leaf 10); the reference's own ICP "
-                                   f"(mp2p_icp/MRPT) is not buildable here"},
+                         "sample": f"{regs} registrations of consecutive 120k-pt scans from constant-velocity guesses, "
+                                   f"one per thread per step (oracle/icp_oracle.c, kd-tree leaf 10); the "
+                                   f"reference's own ICP (mp2p_icp/MRPT) is not buildable here"},
         "e2e": {"value": value, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -219,13 +248,22 @@ def knn_microbench(torch, icp, scans, poses, dev, peak):
     repetition queries a different scan pair (no flush)."""
     out = []
     wp = world_points(scans, poses)
-    clouds = [icp.upload(w) for w in wp]
-    big_xyz = np.concatenate(wp)  # ~1.2M points: the 10 scans in one frame
-    big_raw = icp.upload(big_xyz)
-    big = icp.voxel_decimate(big_raw, 0.1)  # C3's map: merged at 0.1 m
+    clouds = [icp.upload(w) for w in wp[:10]]
+    # C3's local map: every scan of this run in one frame, merged by voxel -- the coarsest of these
+    # resolutions that leaves at least 1,000,000 points (BASELINE config 3: "1M-pt local map")
+    big_raw = icp.upload(np.concatenate(wp))
+    big, map_res = None, None
+    for res in (0.1, 0.07, 0.05, 0.035, 0.025, 0.015):
+        cand = icp.voxel_decimate(big_raw, res)
+        if big is not None:
+            big.free()
+        big, map_res = cand, res
+        if len(big) >= 1_000_000:
+            break
     big_raw.free()
+    log(f"[bench] C3 map: {len(wp)} scans merged at {map_res} m -> {len(big)} points")
     cases = [("120k_vs_120k", 1, clouds, None), ("120k_vs_120k", 6, clouds, None),
-             ("120k_vs_map", 6, clouds, big)]
+             ("120k_vs_1M_map", 6, clouds, big)]
     icp.profile_enable(True)
     for name, k, cl, ref in cases:
         nq = len(cl[0])
@@ -289,7 +327,7 @@ def knn_microbench(torch, icp, scans, poses, dev, peak):
     c3 = {"workload": "c3_scan_to_map", "map_points": len(big), "scan_points": len(sens[0]), "registrations": len(sens),
           "ms_per_registration": ms / len(sens), "registrations_per_s": len(sens) / (ms * 1e-3),
           "mean_matcher_runs": iters / len(sens), "max_abs_translation_error_m": max(errs),
-          "map": "the scans of this run in one frame, merged at 0.1 m (b200icp_voxel_decimate)",
+          "map": f"the {len(wp)} scans of this run in one frame, merged at {map_res} m (b200icp_voxel_decimate)",
           "guess": "true pose + N(0, 0.15 m) / N(0, 0.3 deg yaw)"}
     for c in clouds + sens:
         c.free()
@@ -297,16 +335,15 @@ def knn_microbench(torch, icp, scans, poses, dev, peak):
     return out, c3
 
 
-def batch_lc(torch, dist, capi, lidar_odometry, scans, rank, world, local_rank, dev, pairs_per_gpu, mc=10):
-    """Config C4's shape: candidate pairs of 20k-pt clouds x `mc` Monte-Carlo
-    guesses (sigma 3 m / 2 deg, LidarOdometry.cpp:768-769) with
-    icp-settings-loop-closure.yaml; pair i -> rank i mod world, results
-    gathered with one all-gather."""
+def batch_lc(torch, dist, capi, lidar_odometry, scans, rank, world, local_rank, dev, n_pairs, mc=10):
+    """Config C4: `n_pairs` candidate pairs (1024) of 20k-pt clouds x `mc`
+    Monte-Carlo guesses (sigma 3 m / 2 deg, LidarOdometry.cpp:768-769) with
+    icp-settings-loop-closure.yaml; the SAME pairs at every N, pair i -> rank
+    i mod world (strong scaling), results gathered with one all-gather."""
     from mola_fe_lidar_b200 import multi_gpu as M
     yaml_txt = open(os.path.join(lidar_odometry.PARAMS_DIR, "icp-settings-loop-closure.yaml")).read()
     icp = capi.ICP(yaml_text=yaml_txt, device=local_rank)
     rng = np.random.default_rng(99)  # same on every rank
-    n_pairs = pairs_per_gpu * world
     sub = []
     for s in scans:
         sel = np.sort(rng.choice(len(s), size=20000, replace=False))
@@ -351,7 +388,7 @@ def batch_lc(torch, dist, capi, lidar_odometry, scans, rank, world, local_rank, 
             "registrations_per_s": n_pairs * mc / (ms * 1e-3),
             "outer_iterations_total": float(allrec[:, 8].sum()), "best_quality_mean": float(allrec[:, 6].mean()),
             "sharding": "pair i -> rank i mod N; MC samples of a pair on one rank; one all-gather of results",
-            "scaling": "weak"}
+            "scaling": "strong"}
 
 
 def sharded_knn(torch, dist, capi, scans, poses, rank, world, local_rank, dev, map_per_gpu):
@@ -474,11 +511,7 @@ def run_b200(args, rank, world, local_rank):
         r = icp.align(state["prev"], cur, state["guess"])
         state["prev"].free()
         state["prev"] = cur
-        # constant-velocity guess with equal time steps (LidarOdometry.cpp:272-275, 305-308)
-        back = scan_index(step + 2) < scan_index(step + 1)
-        was_back = scan_index(step + 1) < scan_index(step)
-        g = np.array([r["pose"][0], r["pose"][1], r["pose"][2], r["pose"][3], 0.0, 0.0])
-        state["guess"] = g if back == was_back else np.zeros(6)
+        state["guess"] = next_guess(step, r["pose"])
         state["iters"] += r["n_iterations"] + 1
         state["pairs"] += r["n_pairings"]
         state["rel"].append((scan_index(step), scan_index(step + 1), np.array(r["pose"]), r["quality"]))
@@ -603,7 +636,7 @@ def run_b200(args, rank, world, local_rank):
                 extras["knn"], extras["scan_to_map"] = r
         shared_scans, shared_poses = (scans, poses) if world == 1 else make_scans(1)
         r = section("batch_lc", lambda: batch_lc(torch, dist, capi, lidar_odometry, shared_scans, rank, world,
-                                                 local_rank, dev, args.pairs_per_gpu))
+                                                 local_rank, dev, args.lc_pairs))
         if r is not None:
             extras["batch_lc"] = r
         r = section("sharded_knn", lambda: sharded_knn(torch, dist, capi, shared_scans, shared_poses, rank, world,
@@ -627,13 +660,10 @@ def run_b200(args, rank, world, local_rank):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_value_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 search / f64 solve", "data": "synthetic",
-            "config": {"workload": "c2_kitti64_120k_scan_to_scan_odometry", "points_per_scan": n_pts,
-                       "icp_settings": "icp-settings-regular.yaml via kitti-default.yaml",
-                       "sequences": world, "mean_outer_iterations": mean_iters,
-                       "l2": "inputs (2 x 1.9 MB float4 + index) are L2-resident by nature; each step "
-                             "indexes a different scan, no flush",
-                       "timing": "CUDA events on the legacy default stream bracketing the library's "
-                                 "blocking streams; max over ranks"},
+            "config": workload_config(n_pts),
+            "mean_outer_iterations": mean_iters, "sequences": world,
+            "timing": "CUDA events on the legacy default stream bracketing the library's blocking streams; "
+                      "max over ranks",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "search_tile_kernel<6> (the matcher's kNN search)",
@@ -641,7 +671,7 @@ def run_b200(args, rank, world, local_rank):
                          "avg_launch_ms": avg_ms, "launches_timed": int(prof["match_launches"]),
                          "note": "working set is L2-resident; the kernel is issue/latency bound, see DESIGN.md"},
             "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": n_pts * 12,
-                    "d2h_bytes_per_step": 1128, "ms_per_step": ms_e2e_max / max(e2e_regs / world, 1),
+                    "d2h_bytes_per_step": 1128, "ms_per_step": ms_e2e_max / max(float(u[1]) / world, 1.0),
                     "cuda_graph_replays_rank0": e2e_graph_replays,
                     "api": "LidarOdometry.onNewObservation (b200lo_process_observation), pinned host SoA; "
                            "b200_extra_edge_checks: false (one consecutive-scan registration per scan)"},
@@ -671,23 +701,36 @@ def run_b200(args, rank, world, local_rank):
 
 def cpu_baseline(scans, budget_s=20.0):
     """The oracle port on ONE host thread (how the reference runs one ICP,
-    LidarOdometry.h:167-168), bounded sample of the same workload."""
+    LidarOdometry.h:167-168): a bounded sample of the same workload -- the first
+    scan pairs of the sequence, each from the constant-velocity guess."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_api as O
     O.build()
     prm = O.default_params()
-    clouds = [O.Cloud(s) for s in scans[:4]]
-    for c in clouds:
-        O.knn(c, scans[0][:8], 1, 0.49, kdtree=True)  # lazy kd-tree build, as on first query in MRPT
-    t0, n = time.time(), 0
-    while n < 3 or (time.time() - t0 < budget_s and n < 12):
-        i = n % 3
-        O.icp_align(clouds[i], clouds[i + 1], np.zeros(6), prm, kdtree=True)
-        n += 1
-    dt = time.time() - t0
-    return {"value": n / dt, "unit": "registrations/s", "cores": 1, "kind": "port",
-            "sample": f"{n} registrations of consecutive 120k-pt scans in {dt:.1f}s, 1 thread "
-                      f"(oracle/icp_oracle.c with its kd-tree)"}
+    clouds = {}
+
+    def cloud(i):
+        if i not in clouds:
+            clouds[i] = O.Cloud(scans[i])
+            O.knn(clouds[i], scans[0][:8], 1, 0.49, kdtree=True)  # lazy kd-tree build, as on first query in MRPT
+        return clouds[i]
+
+    cloud(0), cloud(1), cloud(2)
+    r = O.icp_align(cloud(0), cloud(1), np.zeros(6), prm, kdtree=True)  # untimed: gives the first velocity guess
+    guess = next_guess(0, r["pose"])
+    t_all, n, iters, step = 0.0, 0, [], 1
+    while n < 3 or (t_all < budget_s and n < 24):
+        a, b = cloud(scan_index(step)), cloud(scan_index(step + 1))
+        t0 = time.time()
+        r = O.icp_align(a, b, guess, prm, kdtree=True)
+        t_all += time.time() - t0
+        guess = next_guess(step, r["pose"])
+        iters.append(r["n_iterations"] + 1)
+        n, step = n + 1, step + 1
+    return {"value": n / t_all, "unit": "registrations/s", "cores": 1, "kind": "port",
+            "mean_outer_iterations": float(np.mean(iters)),
+            "sample": f"{n} registrations of consecutive 120k-pt scans from constant-velocity guesses in "
+                      f"{t_all:.1f}s, 1 thread (oracle/icp_oracle.c with its kd-tree)"}
 
 
 def main():
@@ -698,7 +741,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the knn / batch_lc / sharded_knn sections")
-    ap.add_argument("--pairs-per-gpu", type=int, default=64, help="C4-shaped section: candidate pairs per GPU")
+    ap.add_argument("--lc-pairs", type=int, default=1024, help="C4 section: candidate pairs in total (sharded over the GPUs)")
     ap.add_argument("--map-points-per-gpu", type=int, default=2_500_000, help="C5-shaped section")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -707,6 +750,8 @@ def main():
     global N_SCANS
     if args.impl == "b200":
         N_SCANS = min(max(10, args.warmup + args.steps + 3), 48)
+    else:  # the same sequence; the threads of the reference arm walk it staggered by one scan each
+        N_SCANS = min(max(10, max(args.warmup, 1) + args.steps + 3 + (os.cpu_count() or 1)), 48)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

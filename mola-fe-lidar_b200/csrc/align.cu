@@ -27,6 +27,7 @@
 // per-pairing Gauss-Newton in exact arithmetic.
 #include "icp_math.cuh"
 #include "tile_search.cuh"
+#include "coop_search.cuh"
 #include "sweep_search.cuh"
 #include "runtime.cuh"
 
@@ -112,15 +113,20 @@ __device__ __forceinline__ bool matcher_active(const IcpDevParams& P, uint32_t i
 // lanes of one warp: lane = query, `has` false on lanes without a point.
 
 // neighbour indices (and squared distances) to a buffer
+// kNN call (by_orig): row = the query's original index, entries = ORIGINAL
+// indices of the neighbours.  Matchers: row = job base + the query's sorted
+// position, entries = SORTED POSITIONS of the neighbours in the global cloud --
+// the fit stage and the next iteration's seeded search read pts[position]
+// directly.
 struct NnWriter
 {
     uint32_t* idx;      // [rows * k]
     float*    d2;       // [rows * k] or null
     uint32_t  k;        // entries per row (<= K)
-    uint32_t  by_orig;  // row = original index of the query (kNN call) | job base + sorted position (matchers)
+    uint32_t  by_orig;
     template <int K>
-    __device__ __forceinline__ void operator()(JobDev& J, bool has, uint32_t pos, uint32_t orig,
-                                               const uint64_t (&key)[K], uint64_t sent) const
+    __device__ __forceinline__ void operator()(JobDev& J, const CloudView& cvG, bool has, uint32_t pos,
+                                               uint32_t orig, const uint64_t (&key)[K], uint64_t sent) const
     {
         if (!has) return;
         const size_t row = by_orig ? (size_t)orig : (size_t)J.pair_base + pos;
@@ -129,7 +135,9 @@ struct NnWriter
             if ((uint32_t)i < k)
             {
                 const bool ok = key[i] != sent;
-                idx[row * k + i] = ok ? key_idx(key[i]) : kInvalid;
+                uint32_t   v = kInvalid;
+                if (ok) v = by_orig ? key_idx(key[i]) : __ldg(cvG.rank + key_idx(key[i]));
+                idx[row * k + i] = v;
                 if (d2) d2[row * k + i] = ok ? key_d2(key[i]) : INFINITY;
             }
     }
@@ -143,7 +151,7 @@ struct KeyWriter
     const uint32_t* map;   // or null
     uint32_t        k;
     template <int K>
-    __device__ __forceinline__ void operator()(JobDev&, bool has, uint32_t, uint32_t orig,
+    __device__ __forceinline__ void operator()(JobDev&, const CloudView&, bool has, uint32_t, uint32_t orig,
                                                const uint64_t (&key)[K], uint64_t sent) const
     {
         if (!has) return;
@@ -178,7 +186,7 @@ struct KeyScatter
     const uint32_t* map;
     uint32_t        k, world, rank, nq, amin, per;
     template <int K>
-    __device__ __forceinline__ void operator()(JobDev&, bool has, uint32_t, uint32_t orig,
+    __device__ __forceinline__ void operator()(JobDev&, const CloudView&, bool has, uint32_t, uint32_t orig,
                                                const uint64_t (&key)[K], uint64_t sent) const
     {
         if (!has) return;
@@ -241,7 +249,7 @@ struct HitCounter
 {
     float thr2;
     template <int K>
-    __device__ __forceinline__ void operator()(JobDev& J, bool has, uint32_t, uint32_t,
+    __device__ __forceinline__ void operator()(JobDev& J, const CloudView&, bool has, uint32_t, uint32_t,
                                                const uint64_t (&key)[K], uint64_t sent) const
     {
         const bool     hit = has && (key[0] != sent) && (key_d2(key[0]) < thr2);
@@ -315,7 +323,7 @@ __global__ void __launch_bounds__(32 * WPI)
                 }
             }
         }
-        if (warp == 0) epi(J, has, first + lane, __float_as_uint(pl.w), key, sent);
+        if (warp == 0) epi(J, cvG, has, first + lane, __float_as_uint(pl.w), key, sent);
         if (WPI > 1) __syncthreads();  // the staging buffers are reused by the next item
     }
 }
@@ -324,17 +332,69 @@ __global__ void __launch_bounds__(32 * WPI)
 __device__ uint32_t* g_dbg_item_cycles = nullptr;
 
 // ---- the per-lane shell walk (tile_search.cuh) as the search stage ----------
+// Neighbour rows of an earlier search of the same queries (the previous outer
+// iteration's matcher run): every entry is a real point of the global cloud, so
+// the k-th smallest of their distances under the CURRENT pose bounds the k-th
+// nearest neighbour from above.  The search then runs with that bound as its
+// radius cap -- all the seeds lie within it, hence so do the true k nearest --
+// and gives exactly the result of the unseeded search (the seeds only bound,
+// they are never inserted).  From the second outer iteration on the pose moves
+// by centimetres: the bound is tight, the shell walk stops at the first shell
+// and empty space is never walked.
+struct SeedRows
+{
+    const uint32_t* rows;  // [job base + sorted position][k] sorted positions in the global cloud; null: none
+    uint32_t        k;
+};
+
+template <int K>
+__device__ __forceinline__ float seeded_cap(const CloudView& cvG, const uint32_t* __restrict__ row, uint32_t sk,
+                                            float qx, float qy, float qz, float cap_d2)
+{
+    if (K == 1)
+    {  // any seed bounds the nearest neighbour
+        float best = cap_d2;
+#pragma unroll
+        for (int i = 0; i < B200ICP_MAX_KNN; i++)
+            if ((uint32_t)i < sk)
+            {
+                const uint32_t p = row[i];
+                if (p != kInvalid) best = fminf(best, dist2(qx, qy, qz, __ldg(cvG.pts + p)));
+            }
+        return best;
+    }
+    if (sk != (uint32_t)K) return cap_d2;
+    float worst = 0.0f;
+#pragma unroll
+    for (int i = 0; i < K; i++)
+    {
+        const uint32_t p = row[i];
+        if (p == kInvalid) return cap_d2;  // fewer than k within the radius last time: no bound
+        worst = fmaxf(worst, dist2(qx, qy, qz, __ldg(cvG.pts + p)));
+    }
+    return fminf(cap_d2, worst);
+}
+
 // Warps draw items from the job's counter (dynamic: the results do not depend
 // on who searches what, and items differ a lot in cost).  Per item (<= 32
 // queries, one per lane): box of the queries' home cells -> tile -> search.
+// Queries the per-lane walk gave up on (candidate budget) are appended to the
+// job's heavy list -- (sorted position, d2 bound) -- and finished by
+// search_heavy_kernel.
+struct HeavyQueue
+{
+    uint32_t* count;   // JobDev::heavy_count
+    uint2*    list;    // this job's entries
+    uint32_t  budget;  // candidates a lane may scan (0xFFFFFFFF: no limit, the queue stays empty)
+};
+
 template <int K, class F>
 __device__ __forceinline__ void for_each_item(WarpTile& W, const CloudView& cvL, const CloudView& cvG,
                                               const GridDev& grid, const double* Rt, uint32_t n_items,
-                                              uint32_t* next_item, float cap_d2, F&& f)
+                                              uint32_t* next_item, float cap_d2, const SeedRows& seed,
+                                              const HeavyQueue& hq, F&& f)
 {
-    const int      lane = threadIdx.x & 31;
-    const int      S = search_shells(grid, cap_d2);
-    const uint64_t sent = sentinel_key(cap_d2);
+    const int lane = threadIdx.x & 31;
     for (;;)
     {
         uint32_t item = 0;
@@ -349,7 +409,17 @@ __device__ __forceinline__ void for_each_item(WarpTile& W, const CloudView& cvL,
         if (has) pl = __ldg(cvL.pts + first + lane);
         double gx, gy, gz;
         transform_point(Rt, pl, gx, gy, gz);
-        const float  qx = (float)gx, qy = (float)gy, qz = (float)gz;
+        const float qx = (float)gx, qy = (float)gy, qz = (float)gz;
+        const bool  finite = has && (fabsf(qx) <= FLT_MAX) && (fabsf(qy) <= FLT_MAX) && (fabsf(qz) <= FLT_MAX);
+        // this lane's radius cap: the caller's, or the tighter bound of its seeds
+        float cap = cap_d2;
+        if (seed.rows && finite)
+            cap = seeded_cap<K>(cvG, seed.rows + (size_t)(first + lane) * seed.k, seed.k, qx, qy, qz, cap_d2);
+        // shells the widest lane of the item may need (warp-uniform)
+        float capmax = finite ? cap : 0.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) capmax = fmaxf(capmax, __shfl_xor_sync(0xFFFFFFFFu, capmax, o));
+        const int       S = search_shells(grid, capmax);
         const QueryCell qc = locate_query(grid, S, qx, qy, qz);
         const bool      hasq = has && qc.valid;
         int lo[3] = {hasq ? qc.hx : INT_MAX, hasq ? qc.hy : INT_MAX, hasq ? qc.hz : INT_MAX};
@@ -360,19 +430,33 @@ __device__ __forceinline__ void for_each_item(WarpTile& W, const CloudView& cvL,
             lo[d] = __reduce_min_sync(0xFFFFFFFFu, lo[d]);
             hi[d] = __reduce_max_sync(0xFFFFFFFFu, hi[d]);
         }
-        TileGeom   G;
-        const bool tiled = warp_tile_build(W, G, cvG, lo, hi, S);
-        uint64_t   key[K];
+        TileGeom       G;
+        const bool     tiled = warp_tile_build(W, G, cvG, lo, hi, S);
+        const uint64_t sent = sentinel_key(cap);
+        uint64_t       key[K];
 #pragma unroll
         for (int i = 0; i < K; i++) key[i] = sent;
+        bool done = true;
         if (hasq)
         {
             if (tiled)
-                tile_knn<K>(W, G, cvG, grid, qc, S, qx, qy, qz, key);
+                done = tile_knn<K>(W, G, cvG, grid, qc, S, qx, qy, qz, hq.budget, key);
             else
-                knn_search<K>(cvG, grid, qx, qy, qz, cap_d2, key);
+                done = knn_search<K>(cvG, grid, qx, qy, qz, cap, hq.budget, key);
         }
-        f(has, first + lane, __float_as_uint(pl.w), key);
+        const unsigned hm = __ballot_sync(0xFFFFFFFFu, !done);
+        if (hm)
+        {   // hand the unfinished queries over, with the best bound this lane has
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(hq.count, (uint32_t)__popc(hm));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (!done)
+            {
+                const float bound = (key[K - 1] != sent) ? key_d2(key[K - 1]) : cap;
+                hq.list[base + __popc(hm & ((1u << lane) - 1u))] = make_uint2(first + lane, __float_as_uint(bound));
+            }
+        }
+        f(has && done, first + lane, __float_as_uint(pl.w), key, sent);
         if (g_dbg_item_cycles && lane == 0)
             g_dbg_item_cycles[item] = (uint32_t)min((long long)0x7FFFFFFF, clock64() - dbg_t0) | (tiled ? 0u : 0x80000000u);
 #ifdef B200ICP_DBG_COUNT
@@ -396,10 +480,17 @@ struct SearchSmem
     uint32_t n_items;
 };
 
+// seed_nn / seed_k: the launch's neighbour-row buffer of an earlier matcher
+// search (rows of job j start at J.pair_base); used when the job says its rows
+// are valid (JobDev::rows_valid, set by the solver after a matcher run).
+#ifndef B200ICP_SEARCH_MINB
+#define B200ICP_SEARCH_MINB 1
+#endif
 template <int K, class Epi>
-__global__ void __launch_bounds__(kChunk)
+__global__ void __launch_bounds__(kChunk, B200ICP_SEARCH_MINB)
     search_tile_kernel(const CloudView* __restrict__ clouds, JobDev* __restrict__ jobs, IcpDevParams P,
-                       float cap_d2, int gate, Epi epi)
+                       float cap_d2, int gate, const uint32_t* seed_nn, uint32_t seed_k, uint2* heavy,
+                       uint32_t budget, Epi epi)
 {
     JobDev& J = jobs[blockIdx.y];
     if (gate == 1 && (J.status != 0 || !matcher_active(P, J.iter))) return;  // matcher: running jobs only
@@ -413,11 +504,59 @@ __global__ void __launch_bounds__(kChunk)
     if (tid == 13) sm.n_items = cvL.grid->n_items;
     __syncthreads();
     const uint32_t n_items = (sm.grid.n_valid > 0) ? sm.n_items : 0u;
-    const uint64_t sent = sentinel_key(cap_d2);
-    for_each_item<K>(sm.tile[tid >> 5], cvL, cvG, sm.grid, sm.Rt, n_items, &J.next_item, cap_d2,
-                     [&](bool has, uint32_t pos, uint32_t orig, uint64_t (&key)[K]) {
-                         epi(J, has, pos, orig, key, sent);
+    SeedRows       seed = {nullptr, seed_k};
+    if (seed_nn && J.rows_valid) seed.rows = seed_nn + (size_t)J.pair_base * seed_k;
+    const HeavyQueue hq = {&J.heavy_count, heavy ? heavy + J.pair_base : nullptr, heavy ? budget : 0xFFFFFFFFu};
+    for_each_item<K>(sm.tile[tid >> 5], cvL, cvG, sm.grid, sm.Rt, n_items, &J.next_item, cap_d2, seed, hq,
+                     [&](bool has, uint32_t pos, uint32_t orig, uint64_t (&key)[K], uint64_t sent) {
+                         epi(J, cvG, has, pos, orig, key, sent);
                      });
+}
+
+// Second pass of a search: the queries of the heavy list, eight lanes each
+// (coop_search.cuh).  Same gates and the same epilogue as the first pass; the
+// list was filled by search_tile_kernel of the same launch pair.
+struct HeavySmem
+{
+    CoopWarpSmem warp[kChunk / 32];
+    GridDev      grid;
+    double       Rt[12];
+};
+
+template <int K, class Epi>
+__global__ void __launch_bounds__(kChunk)
+    search_heavy_kernel(const CloudView* __restrict__ clouds, JobDev* __restrict__ jobs, IcpDevParams P,
+                        int gate, const uint2* __restrict__ heavy, Epi epi)
+{
+    JobDev& J = jobs[blockIdx.y];
+    if (gate == 1 && (J.status != 0 || !matcher_active(P, J.iter))) return;
+    if (gate == 2 && (J.status == 0 || J.evaluated != 0)) return;
+    const uint32_t n_heavy = J.heavy_count;
+    if (n_heavy == 0) return;
+    const CloudView cvL = clouds[J.to_cloud];
+    const CloudView cvG = clouds[J.from_cloud];
+    __shared__ HeavySmem sm;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 12) sm.Rt[tid] = (tid < 9) ? J.R[tid] : J.t[tid - 9];
+    if (tid == 12) sm.grid = *cvG.grid;
+    __syncthreads();
+    const uint2*   list = heavy + J.pair_base;
+    const uint32_t n_tasks = (n_heavy + kSubPerWarp - 1) / kSubPerWarp;
+    for (uint32_t task = item_warp_id(); task < n_tasks; task += item_warp_count())
+    {
+        const uint32_t h = task * kSubPerWarp + (uint32_t)(lane / kSub);
+        const bool     active = h < n_heavy;
+        uint2          e = make_uint2(0u, 0u);
+        if (active) e = list[h];
+        float4 pl = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) pl = __ldg(cvL.pts + e.x);
+        double gx, gy, gz;
+        transform_point(sm.Rt, pl, gx, gy, gz);
+        const float cap = __uint_as_float(e.y);
+        uint64_t    key[K];
+        coop_knn<K>(sm.warp[tid >> 5], cvG, sm.grid, active, (float)gx, (float)gy, (float)gz, cap, key);
+        epi(J, cvG, active && (lane % kSub) == 0, e.x, __float_as_uint(pl.w), key, sentinel_key(cap));
+    }
 }
 
 // ================================================================= fit stage
@@ -546,13 +685,14 @@ __global__ void __launch_bounds__(kChunk, 4)
 
             const uint32_t orig = __float_as_uint(pl.w);
             if (WRITE)
-            {
+            {   // the rows hold sorted positions; the caller gets original indices
                 if (out.nn_cnt) out.nn_cnt[orig] = m;
                 if (out.nn_idx)
 #pragma unroll
                     for (int i = 0; i < K; i++)
                         if ((uint32_t)i < P.knn)
-                            out.nn_idx[(size_t)orig * P.knn + i] = ((uint32_t)i < m) ? nb[i] : kInvalid;
+                            out.nn_idx[(size_t)orig * P.knn + i] =
+                                ((uint32_t)i < m) ? __float_as_uint(__ldg(cvG.pts + nb[i]).w) : kInvalid;
             }
 
             if (m >= P.min_plane_points && m > 0)
@@ -565,8 +705,7 @@ __global__ void __launch_bounds__(kChunk, 4)
                 for (int i = 0; i < K; i++)
                     if ((uint32_t)i < m)
                     {
-                        const uint32_t np = __ldg(cvG.rank + nb[i]);
-                        const float4   pn = __ldg(cvG.pts + np);
+                        const float4 pn = __ldg(cvG.pts + nb[i]);
                         nx_[i] = (double)pn.x, ny_[i] = (double)pn.y, nz_[i] = (double)pn.z;
                         sx += nx_[i], sy += ny_[i], sz += nz_[i];
                     }
@@ -683,9 +822,11 @@ __global__ void __launch_bounds__(kChunk)
         {
             const uint32_t nb = __ldg(nnj + pos);
             const uint32_t orig = __float_as_uint(pl.w);
+            uint32_t       nb_orig = kInvalid;
             if (nb != kInvalid)
             {
-                const float4 pn = __ldg(cvG.pts + __ldg(cvG.rank + nb));
+                const float4 pn = __ldg(cvG.pts + nb);  // the rows hold sorted positions
+                nb_orig = __float_as_uint(pn.w);
                 // the search keeps d2 <= thr^2; the matcher pairs d2 < thr^2
                 paired = dist2((float)gx, (float)gy, (float)gz, pn) < P.thr2;
                 if (paired) q[0] = (double)pn.x, q[1] = (double)pn.y, q[2] = (double)pn.z;
@@ -693,7 +834,7 @@ __global__ void __launch_bounds__(kChunk)
             if (WRITE)
             {
                 if (out.nn_cnt) out.nn_cnt[orig] = paired ? 1u : 0u;
-                if (out.nn_idx) out.nn_idx[orig] = paired ? nb : kInvalid;
+                if (out.nn_idx) out.nn_idx[orig] = paired ? nb_orig : kInvalid;
                 if (out.paired) out.paired[orig] = paired ? 1 : 0;
                 if (paired && out.centroid)
                     out.centroid[(size_t)orig * 3] = q[0], out.centroid[(size_t)orig * 3 + 1] = q[1],
@@ -805,8 +946,9 @@ __global__ void __launch_bounds__(kSolveThreads)
 {
     const uint32_t job = blockIdx.x;
     JobDev&        J = jobs[job];
-    if (threadIdx.x == 0) J.next_item = 0;  // the next search draws items from 0 again
+    if (threadIdx.x == 0) J.next_item = 0, J.heavy_count = 0;  // the next search starts from scratch
     if (J.status != 0) return;
+    if (threadIdx.x == 0 && matcher_active(P, J.iter)) J.rows_valid = 1;  // this iteration's search wrote them
     const int tid = threadIdx.x, lane = tid & 31;
 
     __shared__ double sS[kNumMoments];
@@ -1062,8 +1204,9 @@ __global__ void __launch_bounds__(kSolveThreads)
 {
     const uint32_t job = blockIdx.x;
     JobDev&        J = jobs[job];
-    if (threadIdx.x == 0) J.next_item = 0;  // the next search draws items from 0 again
+    if (threadIdx.x == 0) J.next_item = 0, J.heavy_count = 0;  // the next search starts from scratch
     if (J.status != 0) return;
+    if (threadIdx.x == 0 && matcher_active(P, J.iter)) J.rows_valid = 1;  // this iteration's search wrote them
     const int tid = threadIdx.x;
     __shared__ double sS[kNumMoments];
     __shared__ double sPart[kSolveGroups][kNumMoments];
@@ -1238,6 +1381,9 @@ struct SearchConfig
     bool sweep = false;
     int  wpi = 0;  // 0 = automatic
     bool graphs = true;  // B200ICP_GRAPH=0: no CUDA-graph replay of single registrations
+    bool seeds = true;   // B200ICP_SEED=0: searches never take their bound from the previous neighbour rows
+    uint32_t budget = 96;  // B200ICP_BUDGET: candidates a lane scans before its query goes to the cooperative
+                           // pass (0 = no limit, no second pass)
 };
 static const SearchConfig& search_config()
 {
@@ -1246,6 +1392,8 @@ static const SearchConfig& search_config()
         if (const char* s = getenv("B200ICP_SEARCH")) c.sweep = (strcmp(s, "sweep") == 0);
         if (const char* w = getenv("B200ICP_WPI")) c.wpi = atoi(w);
         if (const char* g = getenv("B200ICP_GRAPH")) c.graphs = atoi(g) != 0;
+        if (const char* g = getenv("B200ICP_SEED")) c.seeds = atoi(g) != 0;
+        if (const char* g = getenv("B200ICP_BUDGET")) c.budget = atoi(g) > 0 ? (uint32_t)atoi(g) : 0xFFFFFFFFu;
         return c;
     }();
     return cfg;
@@ -1282,7 +1430,8 @@ static uint32_t fit_ctas_per_job(const ::b200icp* ctx, size_t max_points, size_t
 template <int K, class Epi>
 static void launch_search_k(const ::b200icp* ctx, Workspace* ws, size_t max_points, size_t njobs,
                             const CloudView* d_clouds, JobDev* d_jobs, const IcpDevParams& D, float cap_d2,
-                            int gate, const Epi& epi)
+                            int gate, const Epi& epi, uint2* d_heavy, const uint32_t* seed_nn = nullptr,
+                            uint32_t seed_k = 0)
 {
     cudaStream_t        s = ws->stream;
     const SearchConfig& cfg = search_config();
@@ -1303,7 +1452,17 @@ static void launch_search_k(const ::b200icp* ctx, Workspace* ws, size_t max_poin
         const size_t   wave = (size_t)ctx->sm_count * resident;
         const size_t   cap = std::max<size_t>(4, (2 * wave + njobs - 1) / njobs);
         const uint32_t G = (uint32_t)std::max<size_t>(1, std::min({(items + warps - 1) / warps, cap, wave}));
-        search_tile_kernel<K, Epi><<<dim3(G, (unsigned)njobs), kChunk, 0, s>>>(d_clouds, d_jobs, D, cap_d2, gate, epi);
+        const uint32_t budget = cfg.budget;
+        uint2*         heavy = (budget != 0xFFFFFFFFu) ? d_heavy : nullptr;
+        search_tile_kernel<K, Epi><<<dim3(G, (unsigned)njobs), kChunk, 0, s>>>(d_clouds, d_jobs, D, cap_d2, gate,
+                                                                              seed_nn, seed_k, heavy, budget, epi);
+        if (heavy)
+        {   // the queries the walk gave up on, eight lanes each; exits at once when there are none
+            const uint32_t GH = (uint32_t)std::max<size_t>(1, std::min(wave, (size_t)G));
+            search_heavy_kernel<K, Epi><<<dim3(GH, (unsigned)njobs), kChunk, 0, s>>>(d_clouds, d_jobs, D, gate, heavy,
+                                                                                    epi);
+            ws->launches++;
+        }
     }
     else
     {
@@ -1332,19 +1491,24 @@ static int matcher_k(const IcpDevParams& D)
 
 // the matcher's search: neighbour rows [job base + sorted position][K]
 static void launch_match_search(const ::b200icp* ctx, Workspace* ws, size_t max_points, size_t njobs,
-                                const CloudView* d_clouds, JobDev* d_jobs, uint32_t* d_nn)
+                                const CloudView* d_clouds, JobDev* d_jobs, uint32_t* d_nn, uint2* d_heavy)
 {
     const IcpDevParams& D = ctx->D;
     const int           K = matcher_k(D);
+    const bool          seeds = search_config().seeds;  // B200ICP_SEED=0: every search from the radius cap
     const NnWriter      w = {d_nn, nullptr, (uint32_t)K, 0u};
     if (K == 1)
-        launch_search_k<1>(ctx, ws, max_points, njobs, d_clouds, d_jobs, D, D.thr2, 1, w);
+        launch_search_k<1>(ctx, ws, max_points, njobs, d_clouds, d_jobs, D, D.thr2, 1, w, d_heavy, seeds ? d_nn : nullptr,
+                           (uint32_t)K);
     else if (K == 4)
-        launch_search_k<4>(ctx, ws, max_points, njobs, d_clouds, d_jobs, D, D.thr2, 1, w);
+        launch_search_k<4>(ctx, ws, max_points, njobs, d_clouds, d_jobs, D, D.thr2, 1, w, d_heavy, seeds ? d_nn : nullptr,
+                           (uint32_t)K);
     else if (K == 6)
-        launch_search_k<6>(ctx, ws, max_points, njobs, d_clouds, d_jobs, D, D.thr2, 1, w);
+        launch_search_k<6>(ctx, ws, max_points, njobs, d_clouds, d_jobs, D, D.thr2, 1, w, d_heavy, seeds ? d_nn : nullptr,
+                           (uint32_t)K);
     else
-        launch_search_k<8>(ctx, ws, max_points, njobs, d_clouds, d_jobs, D, D.thr2, 1, w);
+        launch_search_k<8>(ctx, ws, max_points, njobs, d_clouds, d_jobs, D, D.thr2, 1, w, d_heavy, seeds ? d_nn : nullptr,
+                           (uint32_t)K);
 }
 
 template <bool WRITE>
@@ -1436,6 +1600,7 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
     PairRec*       d_pairs = nullptr;
     double *       d_h0 = nullptr, *d_h1 = nullptr;
     uint32_t*      d_nn = nullptr;
+    uint2*         d_heavy = nullptr;
     Carver sz(nullptr);
     auto layout = [&](Carver& k, CloudView*& dc, JobDev*& dj, double*& dp, uint32_t*& da) {
         dc = k.take<CloudView>(views.size());
@@ -1443,6 +1608,7 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
         dp = k.take<double>((size_t)n * G * kNumMoments);
         da = k.take<uint32_t>(4);
         d_nn = k.take<uint32_t>((total_queries ? total_queries : 1) * (size_t)K);
+        d_heavy = k.take<uint2>(total_queries ? total_queries : 1);
         if (horn)
         {
             d_pairs = k.take<PairRec>(total_queries ? total_queries : 1);
@@ -1492,7 +1658,8 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
     // the same number of iterations -- and checks it right away.
     cudaError_t eval_err = cudaSuccess;
     auto evaluate = [&]() {
-        launch_search_k<1>(ctx, ws, max_points, n, d_clouds, d_jobs, D, D.q_thr2, 2, HitCounter{D.q_thr2});
+        launch_search_k<1>(ctx, ws, max_points, n, d_clouds, d_jobs, D, D.q_thr2, 2, HitCounter{D.q_thr2}, d_heavy,
+                           search_config().seeds ? d_nn : nullptr, (uint32_t)K);
         covariance_kernel<<<(unsigned)n, 64, 0, s>>>(d_jobs, D);
         ws->launches++;
         const cudaError_t e = cudaMemcpyAsync(h_jobs, d_jobs, n * sizeof(JobDev), cudaMemcpyDeviceToHost, s);
@@ -1524,7 +1691,7 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
                 enqueue_setup();
                 for (uint32_t i = 0; i < first; i++)
                 {
-                    launch_match_search(ctx, ws, max_points, n, d_clouds, d_jobs, d_nn);
+                    launch_match_search(ctx, ws, max_points, n, d_clouds, d_jobs, d_nn, d_heavy);
                     launch_fit<false>(ws, D, mgrid, d_clouds, d_jobs, d_nn, d_partials, no_out, d_pairs);
                     solve_kernel<<<(unsigned)n, kSolveThreads, 0, s>>>(d_clouds, d_jobs, d_partials, G, D, d_active);
                     ws->launches++;
@@ -1573,7 +1740,7 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
         for (uint32_t i = 0; i < todo; i++, enq++)
         {
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 0], s));
-            launch_match_search(ctx, ws, max_points, n, d_clouds, d_jobs, d_nn);
+            launch_match_search(ctx, ws, max_points, n, d_clouds, d_jobs, d_nn, d_heavy);
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 1], s));
             launch_fit<false>(ws, D, mgrid, d_clouds, d_jobs, d_nn, d_partials, no_out, d_pairs);
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 2], s));
@@ -1692,6 +1859,7 @@ struct SingleJob
 {
     CloudView* d_clouds = nullptr;
     JobDev*    d_jobs = nullptr;
+    uint2*     d_heavy = nullptr;  // heavy-query list of the search (one entry per query at most)
     Pose       T;
 };
 
@@ -1705,6 +1873,7 @@ static int single_job_setup(Workspace* ws, const b200icp_cloud* from, const b200
     auto layout = [&](Carver& c) {
         sj.d_clouds = c.take<CloudView>(2);
         sj.d_jobs = c.take<JobDev>(1);
+        sj.d_heavy = c.take<uint2>(to->n ? to->n : 1);
         extra(c);
     };
     Carver sz(nullptr);
@@ -1784,13 +1953,13 @@ int run_knn(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, co
 #endif
     }
     if (k == 1)
-        launch_search_k<1>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
+        launch_search_k<1>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
     else if (k <= 4)
-        launch_search_k<4>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
+        launch_search_k<4>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
     else if (k <= 6)
-        launch_search_k<6>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
+        launch_search_k<6>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
     else
-        launch_search_k<8>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
+        launch_search_k<8>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
     if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[1], s));
     B2_CUDA_TRY(cudaGetLastError());
     if (d_dbg)
@@ -1929,13 +2098,13 @@ int run_knn_keys(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* 
     }
     const KeyWriter w = {d_keys_out, d_index_map, k};
     if (k == 1)
-        launch_search_k<1>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
+        launch_search_k<1>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
     else if (k <= 4)
-        launch_search_k<4>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
+        launch_search_k<4>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
     else if (k <= 6)
-        launch_search_k<6>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
+        launch_search_k<6>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
     else
-        launch_search_k<8>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
+        launch_search_k<8>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
     if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[1], s));
     B2_CUDA_TRY(cudaGetLastError());
     B2_CUDA_TRY(cudaStreamSynchronize(s));
@@ -1989,13 +2158,13 @@ static int enqueue_scatter(::b200icp* ctx, Workspace* ws, const b200icp_cloud* r
         B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[0], s));
     }
     if (k == 1)
-        launch_search_k<1>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
+        launch_search_k<1>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
     else if (k <= 4)
-        launch_search_k<4>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
+        launch_search_k<4>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
     else if (k <= 6)
-        launch_search_k<6>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
+        launch_search_k<6>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
     else
-        launch_search_k<8>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
+        launch_search_k<8>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
     if (time_it) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[1], s));
     B2_CUDA_TRY(cudaGetLastError());
     return B200ICP_OK;
@@ -2244,7 +2413,7 @@ int run_match(::b200icp* ctx, const b200icp_cloud* from, const b200icp_cloud* to
     B2_CUDA_TRY(cudaMemsetAsync(mo.nn_idx, 0xFF, n * k * sizeof(uint32_t), s));
     B2_CUDA_TRY(cudaMemsetAsync(mo.centroid, 0, n * 3 * sizeof(double), s));
     B2_CUDA_TRY(cudaMemsetAsync(mo.normal, 0, n * 3 * sizeof(double), s));
-    launch_match_search(ctx, ws, n, 1, sj.d_clouds, sj.d_jobs, d_nn);
+    launch_match_search(ctx, ws, n, 1, sj.d_clouds, sj.d_jobs, d_nn, sj.d_heavy);
     launch_fit<true>(ws, D, dim3(G, 1), sj.d_clouds, sj.d_jobs, d_nn, d_partials, mo, nullptr);
     B2_CUDA_TRY(cudaGetLastError());
     std::vector<double> part((size_t)G * kNumMoments);

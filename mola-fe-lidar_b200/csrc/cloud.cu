@@ -2,9 +2,10 @@
 //
 // Replaces the lazily built nanoflann kd-tree on the `from` cloud
 // (mrpt::math::KDTreeCapable) with a uniform grid:
-//   bbox -> per-point key (30-bit Morton of the block | 6-bit fine cell) ->
-//   radix sort (key, index) -> points gathered as float4 in cell order +
-//   inverse permutation -> scan of fine-cell heads -> open-addressing hash of
+//   bbox -> per-point key (30-bit Morton of the block | 6-bit fine cell |
+//   3-bit octant in the fine cell) -> radix sort (key, index) -> points
+//   gathered as float4 in cell order + inverse permutation + the bounding box
+//   of every group of 8 sorted points -> scan of fine-cell heads -> open-addressing hash of
 //   occupied blocks {start, first fine cell, 64-bit occupancy mask} and the
 //   start offset of every occupied fine cell.
 // Everything after the H2D copy happens on the device with no host sync.
@@ -100,7 +101,7 @@ __global__ void grid_setup_kernel(const uint32_t* __restrict__ bb, float block_r
 }
 
 
-// sort key = (Morton30 of the block) << 6 | fine cell inside the block
+// sort key = Morton30 of the block | fine cell inside the block | octant inside the fine cell
 __global__ void cell_key_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                 const float* __restrict__ z, uint32_t n,
                                 const GridDev* __restrict__ g, unsigned long long* __restrict__ keys,
@@ -112,11 +113,14 @@ __global__ void cell_key_kernel(const float* __restrict__ x, const float* __rest
     unsigned long long key = kInvalidSortKey;
     if (isfinite(px) && isfinite(py) && isfinite(pz))
     {
+        // half-cell coordinates: floor(2u) >> 1 == floor(u) exactly, so the fine
+        // cell is the one the search assumes and the low bit is the octant
         const float    inv = g->inv_cell;
-        const uint32_t fx = (uint32_t)min(max((int)floorf((px - g->ox) * inv), 0), kFineMax);
-        const uint32_t fy = (uint32_t)min(max((int)floorf((py - g->oy) * inv), 0), kFineMax);
-        const uint32_t fz = (uint32_t)min(max((int)floorf((pz - g->oz) * inv), 0), kFineMax);
-        key = fine_sort_key(fx, fy, fz);
+        const int      hmax = 2 * kFineMax + 1;
+        const uint32_t hx = (uint32_t)min(max((int)floorf(((px - g->ox) * inv) * 2.0f), 0), hmax);
+        const uint32_t hy = (uint32_t)min(max((int)floorf(((py - g->oy) * inv) * 2.0f), 0), hmax);
+        const uint32_t hz = (uint32_t)min(max((int)floorf(((pz - g->oz) * inv) * 2.0f), 0), hmax);
+        key = point_sort_key(hx, hy, hz);
     }
     keys[i] = key;
     vals[i] = i;
@@ -128,13 +132,36 @@ __global__ void gather_kernel(const unsigned long long* __restrict__ skeys,
                               const uint32_t* __restrict__ svals, uint32_t n,
                               const float* __restrict__ x, const float* __restrict__ y,
                               const float* __restrict__ z, float4* __restrict__ pts,
-                              uint32_t* __restrict__ rank,
+                              float4* __restrict__ gbox, uint32_t* __restrict__ rank,
                               unsigned long long* __restrict__ flags, GridDev* __restrict__ g)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const unsigned long long key = skeys[j];
-    const uint32_t           i = svals[j];
+    // bounding box of every group of kGroup sorted points: 8 adjacent lanes
+    // (no early return before the shuffles; n is padded by the last warp)
+    const bool               in = j < n;
+    const unsigned long long key = in ? skeys[j] : kInvalidSortKey;
+    const uint32_t           i = in ? svals[j] : 0u;
+    const bool               ok = key < kInvalidSortKey;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (ok) px = x[i], py = y[i], pz = z[i];
+    {
+        float lo[3] = {ok ? px : INFINITY, ok ? py : INFINITY, ok ? pz : INFINITY};
+        float hi[3] = {ok ? px : -INFINITY, ok ? py : -INFINITY, ok ? pz : -INFINITY};
+#pragma unroll
+        for (int o = 1; o < kGroup; o <<= 1)
+#pragma unroll
+            for (int d = 0; d < 3; d++)
+            {
+                lo[d] = fminf(lo[d], __shfl_xor_sync(0xFFFFFFFFu, lo[d], o));
+                hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xFFFFFFFFu, hi[d], o));
+            }
+        if (in && (j % kGroup) == 0)
+        {
+            gbox[2 * (j / kGroup)] = make_float4(lo[0], lo[1], lo[2], 0.f);
+            gbox[2 * (j / kGroup) + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+        }
+    }
+    if (!in) return;
     if (j == 0)
     {  // n_valid = first position holding the invalid key
         uint32_t lo = 0, hi = n;
@@ -154,7 +181,7 @@ __global__ void gather_kernel(const unsigned long long* __restrict__ skeys,
         flags[j] = 0ull;
         return;
     }
-    pts[j] = make_float4(x[i], y[i], z[i], __uint_as_float(i));
+    pts[j] = make_float4(px, py, pz, __uint_as_float(i));
     rank[i] = j;
     // low word: first point of a fine cell; high word: first point of a work
     // item -- one 64-bit scan numbers both.  Items are plain runs of kItem
@@ -162,14 +189,14 @@ __global__ void gather_kernel(const unsigned long long* __restrict__ skeys,
     // straddles far-apart blocks simply takes the per-lane fallback search
     // (measured: cutting at block-group heads as well was slightly slower)
     const unsigned long long prev = j ? skeys[j - 1] : ~0ull;
-    const unsigned long long fine = (j == 0 || prev != key) ? 1ull : 0ull;
+    const unsigned long long fine = (j == 0 || fine_of_key(prev) != fine_of_key(key)) ? 1ull : 0ull;
     const unsigned long long item = ((j % kItem) == 0) ? 1ull : 0ull;
     flags[j] = fine | (item << 32);
 }
 
 __device__ __forceinline__ uint32_t block_key_of(unsigned long long sort_key)
 {
-    const uint32_t mort = (uint32_t)(sort_key >> 6);
+    const uint32_t mort = (uint32_t)block_of_key(sort_key);
     return compact10(mort) | (compact10(mort >> 1) << kGridBits) | (compact10(mort >> 2) << (2 * kGridBits));
 }
 
@@ -183,7 +210,7 @@ __global__ void block_insert_kernel(const unsigned long long* __restrict__ skeys
     if (j >= n) return;
     const unsigned long long key = skeys[j];
     if (key >= kInvalidSortKey) return;
-    if (j != 0 && (skeys[j - 1] >> 6) == (key >> 6)) return;
+    if (j != 0 && block_of_key(skeys[j - 1]) == block_of_key(key)) return;
     const uint32_t bkey = block_key_of(key);
     uint32_t       slot = hash_slot(bkey, hshift);
     for (;;)
@@ -225,8 +252,8 @@ __global__ void fine_publish_kernel(const unsigned long long* __restrict__ skeys
     }
     if (item_flag) item_first[item_ord] = j;
     // the last point of every block publishes the block's end, the first its start
-    const bool blk_last = last || ((skeys[j + 1] >> 6) != (key >> 6));
-    const bool blk_first = (j == 0) || ((skeys[j - 1] >> 6) != (key >> 6));
+    const bool blk_last = last || (block_of_key(skeys[j + 1]) != block_of_key(key));
+    const bool blk_first = (j == 0) || (block_of_key(skeys[j - 1]) != block_of_key(key));
     if (!fine_flag && !blk_last) return;
     const uint32_t bkey = block_key_of(key);
     uint32_t       slot = hash_slot(bkey, hshift);
@@ -236,7 +263,7 @@ __global__ void fine_publish_kernel(const unsigned long long* __restrict__ skeys
     if (!fine_flag) return;
     fine_start[fine_ord] = j;
     unsigned long long* mask = reinterpret_cast<unsigned long long*>(&hrecs[slot].z);
-    atomicOr(mask, 1ull << (uint32_t)(key & 63ull));
+    atomicOr(mask, 1ull << (uint32_t)(fine_of_key(key) & 63ull));
 }
 
 int cloud_alloc(::b200icp* ctx, Workspace* ws, size_t n, float search_radius, b200icp_cloud** out)
@@ -263,6 +290,7 @@ int cloud_alloc(::b200icp* ctx, Workspace* ws, size_t n, float search_radius, b2
     auto layout = [&](Carver& k) {
         c->dx = k.take<float>(nn), c->dy = k.take<float>(nn), c->dz = k.take<float>(nn);
         c->pts = k.take<float4>(nn);
+        c->gbox = k.take<float4>(2 * ((nn + kGroup - 1) / kGroup));
         c->rank = k.take<uint32_t>(nn);
         c->hkeys = k.take<uint32_t>(cap);
         c->hrecs = k.take<uint4>(cap);
@@ -335,7 +363,7 @@ int cloud_build_index(::b200icp* ctx, Workspace* ws, b200icp_cloud* c)
         size_t sort_bytes = 0, scan_bytes = 0;
         cub::DoubleBuffer<unsigned long long> dk(nullptr, nullptr);
         cub::DoubleBuffer<uint32_t>           dv(nullptr, nullptr);
-        B2_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, dk, dv, (int)n, 0, 37, s));
+        B2_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, dk, dv, (int)n, 0, kSortBits, s));
         B2_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (unsigned long long*)nullptr,
                                                   (unsigned long long*)nullptr, (int)n, s));
         const size_t temp_bytes = std::max(sort_bytes, scan_bytes);
@@ -357,9 +385,9 @@ int cloud_build_index(::b200icp* ctx, Workspace* ws, b200icp_cloud* c)
         cell_key_kernel<<<blocks, 256, 0, s>>>(c->dx, c->dy, c->dz, n, c->grid, k0, v0);
         cub::DoubleBuffer<unsigned long long> keys(k0, k1);
         cub::DoubleBuffer<uint32_t>           vals(v0, v1);
-        B2_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, sort_bytes, keys, vals, (int)n, 0, 37, s));
+        B2_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, sort_bytes, keys, vals, (int)n, 0, kSortBits, s));
         gather_kernel<<<blocks, 256, 0, s>>>(keys.Current(), vals.Current(), n, c->dx, c->dy, c->dz,
-                                             c->pts, c->rank, fflag, c->grid);
+                                             c->pts, c->gbox, c->rank, fflag, c->grid);
         B2_CUDA_TRY(cub::DeviceScan::ExclusiveSum(temp, scan_bytes, fflag, ford, (int)n, s));
         block_insert_kernel<<<blocks, 256, 0, s>>>(keys.Current(), n, ford, c->hkeys, c->hrecs,
                                                    c->hshift, c->hcap - 1, c->grid);

@@ -5,7 +5,12 @@
 //   x[n], y[n], z[n]      original order (what the caller uploaded)
 //   pts[n_valid] float4   (x, y, z, bitcast original index), sorted by
 //                         (30-bit Morton code of the point's BLOCK, 6-bit fine
-//                         cell inside the block)
+//                         cell inside the block, 3-bit octant inside the fine
+//                         cell) -- 8 consecutive points of a dense cell are
+//                         spatially compact
+//   gbox[2*ceil(n/8)]     float4 pairs: (min xyz, max xyz) of every GROUP of 8
+//                         consecutive sorted points; the search tests a group's
+//                         box against its current k-th best before loading it
 //   rank[n]               original index -> sorted position
 //   hkeys/hrecs/hrange    open-addressing hash: linear block key -> BlockRec
 //                         {first point, first fine-cell ordinal, 64-bit
@@ -34,6 +39,9 @@ constexpr int kFineMax = 4 * (kGridMax + 1) - 1;  // fine cells per axis - 1
 constexpr int kChunk = 128;    // threads per CTA in the search kernels (4 warps, 4 items in flight)
 constexpr int kItem = 32;      // queries per work item = one warp round
 constexpr int kNumMoments = 192; // three 8x8 tiles of the 16x16 moment matrix S (align.cu)
+constexpr int kMicroBits = 3;   // octant of the point inside its fine cell: low bits of the sort key
+constexpr int kGroup = 8;       // sorted points per bounding-box group
+constexpr int kSortBits = 30 + 6 + kMicroBits + 1;  // Morton30 | fine6 | octant3, +1 for the invalid key
 
 struct GridDev
 {
@@ -51,6 +59,7 @@ struct GridDev
 struct CloudView
 {
     const float4*   pts;
+    const float4*   gbox;        // [2 * groups]: (lo.xyz, -), (hi.xyz, -) of sorted points 8g .. 8g+7
     const uint32_t* rank;
     const GridDev*  grid;
     const uint32_t* hkeys;
@@ -81,6 +90,8 @@ struct JobDev
     uint32_t pair_base;    // first row of this job in the launch's neighbour / pair buffers
     uint32_t next_item;    // work counter of the search stage (reset by the solver)
     uint32_t evaluated;    // quality + covariance taken (once, after the job finished)
+    uint32_t rows_valid;   // the job's neighbour rows hold a matcher search of this registration (seeds)
+    uint32_t heavy_count;  // queries handed to the cooperative pass of the current search (reset by the solver)
 };
 
 struct IcpDevParams
@@ -134,15 +145,22 @@ __host__ __device__ inline uint32_t spread10(uint32_t v)
     return v;
 }
 
-// Sort key of a fine cell (fx,fy,fz in [0, kFineMax]): Morton code of its
-// block in the high bits, position inside the block in the low 6 bits -- the
-// memory order of the index, and the order queries are binned in.
-constexpr unsigned long long kInvalidSortKey = 1ull << 36;
-__host__ __device__ inline unsigned long long fine_sort_key(uint32_t fx, uint32_t fy, uint32_t fz)
+// Sort key of a point from its HALF-cell coordinates (hx,hy,hz in
+// [0, 2*kFineMax+1]; fine cell = h >> 1, octant bit = h & 1): Morton code of the
+// block in the high bits, fine cell inside the block in the next 6 bits, octant
+// inside the fine cell in the low 3 -- the memory order of the index, and the
+// order queries are binned in.  key >> kMicroBits identifies the fine cell,
+// key >> (6 + kMicroBits) the block.
+constexpr unsigned long long kInvalidSortKey = 1ull << (36 + kMicroBits);
+__host__ __device__ inline unsigned long long point_sort_key(uint32_t hx, uint32_t hy, uint32_t hz)
 {
+    const uint32_t fx = hx >> 1, fy = hy >> 1, fz = hz >> 1;
     const uint32_t mort = spread10(fx >> 2) | (spread10(fy >> 2) << 1) | (spread10(fz >> 2) << 2);
     const uint32_t sub = (fx & 3u) | ((fy & 3u) << 2) | ((fz & 3u) << 4);
-    return ((unsigned long long)mort << 6) | sub;
+    const uint32_t oct = (hx & 1u) | ((hy & 1u) << 1) | ((hz & 1u) << 2);
+    return ((((unsigned long long)mort << 6) | sub) << kMicroBits) | oct;
 }
+__host__ __device__ inline unsigned long long fine_of_key(unsigned long long k) { return k >> kMicroBits; }
+__host__ __device__ inline unsigned long long block_of_key(unsigned long long k) { return k >> (6 + kMicroBits); }
 
 }  // namespace b2

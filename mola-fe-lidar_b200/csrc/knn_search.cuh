@@ -16,10 +16,6 @@
 #pragma once
 #include "device_types.cuh"
 
-#ifndef B200ICP_SCAN8
-#define B200ICP_SCAN8 1
-#endif
-
 namespace b2
 {
 #ifdef B200ICP_DBG_COUNT
@@ -111,43 +107,32 @@ __device__ __forceinline__ float dist2(float qx, float qy, float qz, const float
     return ab + e;  // A.3: ((dx^2 + dy^2) + dz^2), no contraction
 }
 
-// all points of one fine cell, [beg,end) in the sorted array
-template <int K>
-__device__ __forceinline__ void scan_range(const float4* __restrict__ pts, uint32_t beg,
-                                           uint32_t end, float qx, float qy, float qz,
-                                           uint64_t (&key)[K])
+// Lower bound of dist2(q, p) over every point p inside the box [lo, hi], in
+// the SAME operation order as dist2.  Every step (difference, square, sums) is
+// monotonic under round-to-nearest and the library is built without FMA
+// contraction, so box_lower_d2 <= dist2(q, p) holds for the COMPUTED values,
+// not just in exact arithmetic: a group whose bound exceeds the current k-th
+// best d2 cannot change the result, ties included.
+__device__ __forceinline__ float box_lower_d2(float qx, float qy, float qz, const float4& lo, const float4& hi)
 {
-#ifdef B200ICP_DBG_COUNT
-    if (g_dbg_lane_cand) g_dbg_lane_cand[(blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x] += end - beg;
-#endif
+    const float dx = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.0f);
+    const float dy = fmaxf(fmaxf(lo.y - qy, qy - hi.y), 0.0f);
+    const float dz = fmaxf(fmaxf(lo.z - qz, qz - hi.z), 0.0f);
+    const float a = dx * dx;
+    const float b = dy * dy;
+    const float e = dz * dz;
+    const float ab = a + b;
+    return ab + e;
+}
+
+// a short run, point by point (four independent loads in flight)
+template <int K>
+__device__ __forceinline__ void scan_plain(const float4* __restrict__ pts, uint32_t beg, uint32_t end,
+                                           float qx, float qy, float qz, uint64_t (&key)[K])
+{
     uint32_t j = beg;
-#if B200ICP_SCAN8
-    for (; j + 8 <= end; j += 8)
-    {
-        // long runs (dense cells) are latency bound: eight independent loads in flight
-        float4 c[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) c[u] = __ldg(pts + j + u);
-        uint64_t kk[8];
-        bool     any = false;
-        const uint64_t w = key[K - 1];
-#pragma unroll
-        for (int u = 0; u < 8; u++)
-        {
-            kk[u] = make_key(dist2(qx, qy, qz, c[u]), __float_as_uint(c[u].w));
-            any |= kk[u] < w;
-        }
-        if (any)
-        {
-#pragma unroll
-            for (int u = 0; u < 8; u++)
-                if (kk[u] < key[K - 1]) topk_insert<K>(key, kk[u]);
-        }
-    }
-#endif
     for (; j + 4 <= end; j += 4)
     {
-        // four independent loads in flight before the first use
         const float4   c0 = __ldg(pts + j), c1 = __ldg(pts + j + 1), c2 = __ldg(pts + j + 2),
                      c3 = __ldg(pts + j + 3);
         const uint64_t k0 = make_key(dist2(qx, qy, qz, c0), __float_as_uint(c0.w));
@@ -171,18 +156,76 @@ __device__ __forceinline__ void scan_range(const float4* __restrict__ pts, uint3
     }
 }
 
-// keys must be initialised by the caller with sentinel_key(cap_d2).
+#ifndef B200ICP_PLAIN_RUN
+#define B200ICP_PLAIN_RUN 6
+#endif
+constexpr uint32_t kPlainRun = B200ICP_PLAIN_RUN;  // runs up to this length are scanned without looking at group boxes
+
+// All points of one fine cell, [beg,end) in the sorted array.  Longer runs go
+// GROUP by group (kGroup = 8 consecutive sorted points, spatially compact
+// because points are sorted by octant inside the cell): the group's bounding
+// box is tested against the current k-th best first -- in a dense cell most
+// groups are rejected with two 16-byte loads instead of eight -- and a group
+// that survives is loaded whole (eight independent loads in flight).
 template <int K>
-__device__ __forceinline__ void knn_search(const CloudView& cv, const GridDev& g, float qx,
-                                           float qy, float qz, float cap_d2,
+__device__ __forceinline__ void scan_range(const float4* __restrict__ pts, const float4* __restrict__ gbox,
+                                           uint32_t beg, uint32_t end, float qx, float qy, float qz,
                                            uint64_t (&key)[K])
 {
+#ifdef B200ICP_DBG_COUNT
+    if (g_dbg_lane_cand) g_dbg_lane_cand[(blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x] += end - beg;
+#endif
+    if (end - beg <= kPlainRun)
+    {
+        scan_plain<K>(pts, beg, end, qx, qy, qz, key);
+        return;
+    }
+    const uint32_t g1 = (end - 1) / kGroup;
+    for (uint32_t g = beg / kGroup; g <= g1; g++)
+    {
+        const float4 lo = __ldg(gbox + 2 * g), hi = __ldg(gbox + 2 * g + 1);
+        if (box_lower_d2(qx, qy, qz, lo, hi) > key_d2(key[K - 1])) continue;
+        const uint32_t base = g * kGroup;
+        float4         c[kGroup];
+#pragma unroll
+        for (int u = 0; u < kGroup; u++)
+        {
+            // points of the neighbouring cells that share the group are loaded but masked below
+            const uint32_t j = min(max(base + u, beg), end - 1);
+            c[u] = __ldg(pts + j);
+        }
+        uint64_t       kk[kGroup];
+        bool           any = false;
+        const uint64_t w = key[K - 1];
+#pragma unroll
+        for (int u = 0; u < kGroup; u++)
+        {
+            const bool in = (base + u >= beg) && (base + u < end);
+            kk[u] = in ? make_key(dist2(qx, qy, qz, c[u]), __float_as_uint(c[u].w)) : ~0ull;
+            any |= kk[u] < w;
+        }
+        if (any)
+        {
+#pragma unroll
+            for (int u = 0; u < kGroup; u++)
+                if (kk[u] < key[K - 1]) topk_insert<K>(key, kk[u]);
+        }
+    }
+}
+
+// keys must be initialised by the caller with sentinel_key(cap_d2).
+template <int K>
+__device__ __forceinline__ bool knn_search(const CloudView& cv, const GridDev& g, float qx,
+                                           float qy, float qz, float cap_d2, uint32_t budget,
+                                           uint64_t (&key)[K])
+{
+    uint32_t used = 0;
     const float inv = g.inv_cell;
     // shells of fine cells that can hold a point within the cap
     const int   S = max(1, (int)ceilf(sqrtf(cap_d2) * inv * 1.0005f));
     const float lim_lo = -(float)(S + 2), lim_hi = (float)(kFineMax + S + 3);
     float       ux = (qx - g.ox) * inv, uy = (qy - g.oy) * inv, uz = (qz - g.oz) * inv;
-    if (!(ux == ux) || !(uy == uy) || !(uz == uz)) return;  // NaN query: no neighbours
+    if (!(ux == ux) || !(uy == uy) || !(uz == uz)) return true;  // NaN query: no neighbours
     ux = fminf(fmaxf(ux, lim_lo), lim_hi);
     uy = fminf(fmaxf(uy, lim_lo), lim_hi);
     uz = fminf(fmaxf(uz, lim_lo), lim_hi);
@@ -243,13 +286,16 @@ __device__ __forceinline__ void knn_search(const CloudView& cv, const GridDev& g
                         const uint32_t ord = rec.y + (uint32_t)__popcll(occ & ((1ull << bit) - 1ull));
                         const uint32_t beg = __ldg(cv.fine_start + ord);
                         const uint32_t end = __ldg(cv.fine_start + ord + 1);
-                        scan_range<K>(cv.pts, beg, end, qx, qy, qz, key);
+                        scan_range<K>(cv.pts, cv.gbox, beg, end, qx, qy, qz, key);
                         worst = key_d2(key[K - 1]) * to_cells2;
+                        used += end - beg;
+                        if (used > budget) return false;
                     }
                 }
             }
         }
     }
+    return true;
 }
 
 }  // namespace b2

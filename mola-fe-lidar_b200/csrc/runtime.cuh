@@ -157,6 +157,7 @@ struct b200icp_cloud
     size_t   slab_bytes = 0;
     float *  dx = nullptr, *dy = nullptr, *dz = nullptr;
     float4*  pts = nullptr;
+    float4*  gbox = nullptr;
     uint32_t* rank = nullptr;
     uint32_t* hkeys = nullptr;
     uint4*    hrecs = nullptr;
@@ -172,7 +173,7 @@ struct b200icp_cloud
     b2::CloudView view() const
     {
         b2::CloudView v;
-        v.pts = pts, v.rank = rank, v.grid = grid, v.hkeys = hkeys, v.hrecs = hrecs, v.hrange = hrange;
+        v.pts = pts, v.gbox = gbox, v.rank = rank, v.grid = grid, v.hkeys = hkeys, v.hrecs = hrecs, v.hrange = hrange;
         v.fine_start = fine_start;
         v.item_first = item_first;
         v.hshift = hshift, v.hmask = hcap - 1, v.n = (uint32_t)n;

@@ -12,7 +12,17 @@
 
 struct b200icp { b200icp_params_t P; };
 struct b200icp_cloud { size_t n; float p0[3]; };
-static unsigned long g_align_calls = 0, g_batch_calls = 0, g_voxel_calls = 0;
+static unsigned long g_align_calls = 0, g_batch_calls = 0, g_voxel_calls = 0, g_upload_calls = 0;
+const char* b200icp_last_error(void) { return "test double: no error"; }
+void b200icp_default_params(b200icp_params_t* p)
+{
+    memset(p, 0, sizeof(*p));
+    p->max_iterations = 100, p->min_abs_step_trans = 5e-5, p->min_abs_step_rot = 1e-5;
+    p->solver_max_iterations = 20, p->gn_min_delta = 1e-10, p->distance_threshold = 0.7;
+    p->plane_eigen_threshold = 0.07, p->knn = 6, p->min_plane_points = 3;
+    p->quality_threshold_distance = 0.1, p->cov_fd_step = 1e-7;
+    p->use_scale_outlier_detector = 1, p->scale_outlier_threshold = 1.1, p->robust_kernel_scale = 400.0;
+}
 
 int b200icp_device_count(void) { return 1; }
 int b200icp_create(const b200icp_params_t* p, int device, b200icp_t** out)
@@ -32,6 +42,32 @@ int b200icp_cloud_upload(b200icp_t* icp, const float* x, const float* y, const f
     c->n = n;
     if (n) c->p0[0] = x[0], c->p0[1] = y[0], c->p0[2] = z[0];
     *out = c;
+    __atomic_add_fetch(&g_upload_calls, 1, __ATOMIC_RELAXED);
+    return B200ICP_OK;
+}
+unsigned long fake_upload_calls(void) { return g_upload_calls; }
+/* "match": every second local point is paired; its plane is (first local point + i * 0.01 along x, moved by the
+ * translation of the pose; normal +z) */
+int b200icp_match(b200icp_t* icp, const b200icp_cloud_t* from_global, const b200icp_cloud_t* to_local,
+                  const double* pose6, uint8_t* paired, uint32_t* nn_idx, uint32_t* nn_cnt, double* centroid,
+                  double* normal, uint32_t* n_pairings)
+{
+    (void)icp, (void)from_global, (void)nn_idx, (void)nn_cnt;
+    uint32_t np = 0;
+    for (size_t i = 0; i < to_local->n; i++)
+    {
+        const int p = (i % 2) == 0;
+        if (paired) paired[i] = (uint8_t)p;
+        np += (uint32_t)p;
+        if (centroid)
+        {
+            centroid[3 * i] = (double)to_local->p0[0] + 0.01 * (double)i + (pose6 ? pose6[0] : 0.0);
+            centroid[3 * i + 1] = (double)to_local->p0[1] + (pose6 ? pose6[1] : 0.0);
+            centroid[3 * i + 2] = (double)to_local->p0[2] + (pose6 ? pose6[2] : 0.0);
+        }
+        if (normal) normal[3 * i] = 0.0, normal[3 * i + 1] = 0.0, normal[3 * i + 2] = 1.0;
+    }
+    if (n_pairings) *n_pairings = np;
     return B200ICP_OK;
 }
 void   b200icp_cloud_free(b200icp_cloud_t* c) { free(c); }
@@ -76,7 +112,7 @@ int b200icp_align(b200icp_t* icp, const b200icp_cloud_t* from, const b200icp_clo
                   const double guess6[6], b200icp_result_t* out)
 {
     (void)icp;
-    g_align_calls++;
+    __atomic_add_fetch(&g_align_calls, 1, __ATOMIC_RELAXED);
     fake_result(from, to, guess6, out);
     return B200ICP_OK;
 }

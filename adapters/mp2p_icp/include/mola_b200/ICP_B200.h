@@ -46,6 +46,7 @@ class ICP_B200 : public mp2p_icp::ICP
     b200icp_params_t translate(const mp2p_icp::Parameters& p) const;
 
     std::size_t cachedClouds() const { return clouds_.size(); }
+    std::size_t contexts() const { return ctxs_.size(); }
     std::size_t uploads() const { return clouds_.uploads(); }
 
    private:
@@ -57,7 +58,7 @@ class ICP_B200 : public mp2p_icp::ICP
         b200icp_t*       h;
     };
     std::mutex                   mtx_;
-    std::vector<Ctx>             ctxs_;  // one device context per distinct parameter block seen
+    std::vector<Ctx>             ctxs_;  // one device context per distinct solver / matcher / quality configuration
     mola_b200::DeviceCloudCache  clouds_;
     int                          device_ = 0;
     std::string                  layer_  = mp2p_icp::metric_map_t::PT_LAYER_RAW;

@@ -15,13 +15,11 @@ namespace
 {
 [[noreturn]] void fail(const std::string& what) { throw std::runtime_error("mola::ICP_B200: " + what); }
 
-bool same_params(const b200icp_params_t& a, const b200icp_params_t& b)
+// the part of the block that belongs to the OBJECT (solvers, matchers, quality evaluators); the rest is
+// mp2p_icp::Parameters and travels with each call (b200icp_align_with)
+bool same_object_params(const b200icp_params_t& a, const b200icp_params_t& b)
 {
-    return a.max_iterations == b.max_iterations && a.min_abs_step_trans == b.min_abs_step_trans &&
-           a.min_abs_step_rot == b.min_abs_step_rot && a.use_scale_outlier_detector == b.use_scale_outlier_detector &&
-           a.scale_outlier_threshold == b.scale_outlier_threshold && a.use_robust_kernel == b.use_robust_kernel &&
-           a.robust_kernel_param == b.robust_kernel_param && a.robust_kernel_scale == b.robust_kernel_scale &&
-           a.solver_kind == b.solver_kind && a.solver_max_iterations == b.solver_max_iterations &&
+    return a.solver_kind == b.solver_kind && a.solver_max_iterations == b.solver_max_iterations &&
            a.gn_min_delta == b.gn_min_delta && a.matcher_kind == b.matcher_kind &&
            a.distance_threshold == b.distance_threshold && a.plane_eigen_threshold == b.plane_eigen_threshold &&
            a.knn == b.knn && a.min_plane_points == b.min_plane_points &&
@@ -99,7 +97,7 @@ b200icp_t* ICP_B200::context_for(const b200icp_params_t& q)
 {
     std::lock_guard<std::mutex> lk(mtx_);
     for (auto& c : ctxs_)
-        if (same_params(c.q, q)) return c.h;
+        if (same_object_params(c.q, q)) return c.h;
     b200icp_t* h = nullptr;
     if (b200icp_create(&q, device_, &h) != B200ICP_OK) fail(std::string("b200icp_create: ") + b200icp_last_error());
     ctxs_.push_back({q, h});
@@ -109,8 +107,12 @@ b200icp_t* ICP_B200::context_for(const b200icp_params_t& q)
 void ICP_B200::align(const mp2p_icp::metric_map_t& pc1, const mp2p_icp::metric_map_t& pc2,
                      const mrpt::math::TPose3D& guess, const mp2p_icp::Parameters& p, mp2p_icp::Results& result)
 {
-    // the reference passes icp_params per call (cpp:871; chosen at cpp:287-290), the lists live in the object
-    b200icp_t* h = context_for(translate(p));
+    // the reference passes icp_params per call (cpp:871; chosen at cpp:287-290), the lists live in the object:
+    // one device context per object configuration, the call's Parameters go with the call
+    const b200icp_params_t q = translate(p);
+    b200icp_t*             h = context_for(q);
+    b200icp_call_params_t  call;
+    b200icp_call_params_of(&q, &call);
 
     const auto global = pc1.point_layer(layer_);
     const auto local  = pc2.point_layer(layer_);
@@ -120,8 +122,8 @@ void ICP_B200::align(const mp2p_icp::metric_map_t& pc1, const mp2p_icp::metric_m
 
     const double     g6[6] = {guess.x, guess.y, guess.z, guess.yaw, guess.pitch, guess.roll};
     b200icp_result_t r;
-    if (b200icp_align(h, g->cloud, l->cloud, g6, &r) != B200ICP_OK)
-        fail(std::string("b200icp_align: ") + b200icp_last_error());
+    if (b200icp_align_with(h, g->cloud, l->cloud, g6, &call, &r) != B200ICP_OK)
+        fail(std::string("b200icp_align_with: ") + b200icp_last_error());
 
     result = mp2p_icp::Results();
     result.optimal_tf.mean = mrpt::poses::CPose3D(r.pose[0], r.pose[1], r.pose[2], r.pose[3], r.pose[4], r.pose[5]);

@@ -78,6 +78,22 @@ typedef struct b200icp_params
     double   cov_fd_step;
 } b200icp_params_t;
 
+/* mp2p_icp::Parameters, the part of the block above that the reference hands to EVERY align() call next to the
+ * shared ICP object (in.icp_params, LidarOdometry.cpp:869-871; chosen per scan at cpp:287-290): the iteration
+ * budget, the step tolerances and pairingsWeightParameters.  Solvers, matchers and quality evaluators belong to
+ * the object (initialize_solvers / _matchers / _quality_evaluators, cpp:80-87) and are not part of a call. */
+typedef struct b200icp_call_params
+{
+    uint32_t max_iterations;
+    double   min_abs_step_trans;
+    double   min_abs_step_rot;
+    int32_t  use_scale_outlier_detector;
+    double   scale_outlier_threshold;
+    int32_t  use_robust_kernel;
+    double   robust_kernel_param;
+    double   robust_kernel_scale;
+} b200icp_call_params_t;
+
 /* mp2p_icp::Results as consumed at LidarOdometry.cpp:873-888:
  * optimal_tf {mean, cov}, quality, nIterations, terminationReason. */
 typedef struct b200icp_result
@@ -96,7 +112,7 @@ typedef struct b200icp_result
 /* per-kernel device timings, CUDA events on the launching stream */
 typedef struct b200icp_profile
 {
-    uint64_t match_launches;  /* the matcher's search kernel: transform + exact kNN (tile sweep) */
+    uint64_t match_launches;  /* the matcher's search: transform + exact kNN (per-lane shell walk + cooperative pass) */
     double   match_ms;
     uint64_t match_queries;   /* queries processed by those launches */
     uint64_t solve_launches;
@@ -260,6 +276,12 @@ int b200icp_match(b200icp_t* icp, const b200icp_cloud_t* from_global,
 int b200icp_align(b200icp_t* icp, const b200icp_cloud_t* from_global,
                   const b200icp_cloud_t* to_local, const double guess6[6],
                   b200icp_result_t* out);
+/* The same with the call's own mp2p_icp::Parameters (NULL = the object's): what icp->align(from, to, guess,
+ * in.icp_params, result) means at cpp:869-871 -- the object's matchers / solvers / quality evaluators, the
+ * caller's iteration budget, tolerances and pairing weights.  No device object is created or destroyed. */
+void b200icp_call_params_of(const b200icp_params_t* p, b200icp_call_params_t* out);
+int  b200icp_align_with(b200icp_t* icp, const b200icp_cloud_t* from_global, const b200icp_cloud_t* to_local,
+                        const double guess6[6], const b200icp_call_params_t* call, b200icp_result_t* out);
 /* n independent registrations in lock-step launches (worker_pool_past_KFs_
  * jobs cpp:711-729 and the Monte-Carlo loop cpp:775-787). Cloud handles may
  * repeat (their indices are shared). guesses = [n*6]. */

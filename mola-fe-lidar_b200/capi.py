@@ -51,6 +51,20 @@ class Params(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class CallParams(C.Structure):
+    """b200icp_call_params_t: mp2p_icp::Parameters of one align() call (LidarOdometry.cpp:869-871)."""
+    _fields_ = [
+        ("max_iterations", C.c_uint32),
+        ("min_abs_step_trans", C.c_double),
+        ("min_abs_step_rot", C.c_double),
+        ("use_scale_outlier_detector", C.c_int32),
+        ("scale_outlier_threshold", C.c_double),
+        ("use_robust_kernel", C.c_int32),
+        ("robust_kernel_param", C.c_double),
+        ("robust_kernel_scale", C.c_double),
+    ]
+
+
 class Result(C.Structure):
     _fields_ = [
         ("pose", C.c_double * 6),
@@ -95,7 +109,7 @@ EXPORTS = [
     "b200icp_voxel_decimate", "b200icp_knn", "b200icp_knn_keys_device", "b200icp_merge_keys_device",
     "b200icp_knn_keys_scatter", "b200icp_peer_alloc", "b200icp_peer_free", "b200icp_peer_open",
     "b200icp_peer_close", "b200icp_peer_barrier", "b200icp_knn_keys_exchange", "b200icp_fill_no_key",
-    "b200icp_match", "b200icp_align",
+    "b200icp_match", "b200icp_align", "b200icp_align_with", "b200icp_call_params_of",
     "b200icp_align_batch", "b200icp_profile_enable", "b200icp_profile_reset",
     "b200icp_profile_get", "b200icp_synchronize",
 ]
@@ -149,6 +163,9 @@ def lib():
     L.b200icp_fill_no_key.argtypes = [vp, vp, C.c_size_t]
     L.b200icp_match.argtypes = [vp, vp, vp, dp, C.POINTER(C.c_uint8), up, up, dp, dp, up]
     L.b200icp_align.argtypes = [vp, vp, vp, dp, C.POINTER(Result)]
+    L.b200icp_align_with.argtypes = [vp, vp, vp, dp, C.POINTER(CallParams), C.POINTER(Result)]
+    L.b200icp_call_params_of.argtypes = [C.POINTER(Params), C.POINTER(CallParams)]
+    L.b200icp_call_params_of.restype = None
     L.b200icp_align_batch.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(vp), dp,
                                       C.POINTER(Result)]
     L.b200icp_profile_enable.argtypes = [vp, C.c_int]
@@ -376,6 +393,23 @@ class ICP:
         r = Result()
         _check(lib().b200icp_align(self.h, from_global.h, to_local.h, _ptr(g, C.c_double),
                                    C.byref(r)))
+        return r.as_dict()
+
+    def align_with(self, from_global, to_local, guess6=None, **call):
+        """b200icp_align_with: the object's matchers / solvers / quality evaluators with this call's own
+        mp2p_icp::Parameters; keyword arguments override fields of the object's parameter block."""
+        g = np.ascontiguousarray(np.zeros(6) if guess6 is None else guess6, dtype=np.float64)
+        base = Params()
+        _check(lib().b200icp_get_params(self.h, C.byref(base)))
+        cp = CallParams()
+        lib().b200icp_call_params_of(C.byref(base), C.byref(cp))
+        for k, v in call.items():
+            if not hasattr(cp, k):
+                raise KeyError(k)
+            setattr(cp, k, v)
+        r = Result()
+        _check(lib().b200icp_align_with(self.h, from_global.h, to_local.h, _ptr(g, C.c_double), C.byref(cp),
+                                        C.byref(r)))
         return r.as_dict()
 
     def align_batch(self, from_list, to_list, guesses):

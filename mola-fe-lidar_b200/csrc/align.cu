@@ -2,20 +2,20 @@
 // drives it (LidarOdometry.cpp:869-871),
 // resident on the device for the whole iteration loop.
 //
-// Per outer iteration, three launches over a table of independent jobs:
+// Per outer iteration, two launches over a table of independent jobs:
 //   search kernel : per local point -- transform (A.2), radius-capped exact
-//                   kNN on the grid index (A.3/A.4): the tile sweep of
-//                   sweep_search.cuh, one CTA per 32-query item, scheduled
-//                   dynamically (results do not depend on the order) -> the
-//                   neighbour rows nn[job][point][K].
+//                   kNN on the grid index (A.3/A.4): the per-lane shell walk of
+//                   tile_search.cuh over 32-query items, scheduled dynamically
+//                   (results do not depend on the order), from the second
+//                   iteration on bounded by the previous neighbours re-measured
+//                   under the new pose -> the neighbour rows nn[job][point][K].
 //   fit kernel    : per local point -- plane fit + gates (A.5) and the
-//                   point-to-plane MOMENTS of the pairing, accumulated per warp
-//                   over a STATIC list of items and reduced per CTA in a
-//                   fixed-shape tree to partials[job][cta][192] (f64).
-//   solve_kernel  : fixed-order reduction of the partials, then the whole
-//                   Gauss-Newton inner loop (A.6) on the 12x12 moment matrix,
-//                   the SE(3) update, the convergence test (A.7) and the job's
-//                   status flags -- no host round trip.
+//                   point-to-plane MOMENTS of the pairing, accumulated per chunk
+//                   of items and reduced in a fixed tree over the data; the warp
+//                   that completes a job's reduction runs the whole Gauss-Newton
+//                   inner loop (A.6) on the 12x12 moment matrix, the SE(3)
+//                   update, the convergence test (A.7) and sets the job's status
+//                   flags -- no separate solver launch, no host round trip.
 //
 // Why moments: the point-to-plane residual r_i(T) = n_i.(R p_i + t - c_i) is
 // LINEAR in theta = (R row-major | t) interleaved as 3 rows of (R_i0 R_i1 R_i2 t_i):
@@ -27,7 +27,6 @@
 // per-pairing Gauss-Newton in exact arithmetic.
 #include "icp_math.cuh"
 #include "tile_search.cuh"
-#include "coop_search.cuh"
 #include "sweep_search.cuh"
 #include "runtime.cuh"
 
@@ -378,21 +377,10 @@ __device__ __forceinline__ float seeded_cap(const CloudView& cvG, const uint32_t
 // Warps draw items from the job's counter (dynamic: the results do not depend
 // on who searches what, and items differ a lot in cost).  Per item (<= 32
 // queries, one per lane): box of the queries' home cells -> tile -> search.
-// Queries the per-lane walk gave up on (candidate budget) are appended to the
-// job's heavy list -- (sorted position, d2 bound) -- and finished by
-// search_heavy_kernel.
-struct HeavyQueue
-{
-    uint32_t* count;   // JobDev::heavy_count
-    uint2*    list;    // this job's entries
-    uint32_t  budget;  // candidates a lane may scan (0xFFFFFFFF: no limit, the queue stays empty)
-};
-
 template <int K, class F>
 __device__ __forceinline__ void for_each_item(WarpTile& W, const CloudView& cvL, const CloudView& cvG,
                                               const GridDev& grid, const double* Rt, uint32_t n_items,
-                                              uint32_t* next_item, float cap_d2, const SeedRows& seed,
-                                              const HeavyQueue& hq, F&& f)
+                                              uint32_t* next_item, float cap_d2, const SeedRows& seed, F&& f)
 {
     const int lane = threadIdx.x & 31;
     for (;;)
@@ -436,27 +424,14 @@ __device__ __forceinline__ void for_each_item(WarpTile& W, const CloudView& cvL,
         uint64_t       key[K];
 #pragma unroll
         for (int i = 0; i < K; i++) key[i] = sent;
-        bool done = true;
         if (hasq)
         {
             if (tiled)
-                done = tile_knn<K>(W, G, cvG, grid, qc, S, qx, qy, qz, hq.budget, key);
+                tile_knn<K>(W, G, cvG, grid, qc, S, qx, qy, qz, key);
             else
-                done = knn_search<K>(cvG, grid, qx, qy, qz, cap, hq.budget, key);
+                knn_search<K>(cvG, grid, qx, qy, qz, cap, key);
         }
-        const unsigned hm = __ballot_sync(0xFFFFFFFFu, !done);
-        if (hm)
-        {   // hand the unfinished queries over, with the best bound this lane has
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(hq.count, (uint32_t)__popc(hm));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (!done)
-            {
-                const float bound = (key[K - 1] != sent) ? key_d2(key[K - 1]) : cap;
-                hq.list[base + __popc(hm & ((1u << lane) - 1u))] = make_uint2(first + lane, __float_as_uint(bound));
-            }
-        }
-        f(has && done, first + lane, __float_as_uint(pl.w), key, sent);
+        f(has, first + lane, __float_as_uint(pl.w), key, sent);
         if (g_dbg_item_cycles && lane == 0)
             g_dbg_item_cycles[item] = (uint32_t)min((long long)0x7FFFFFFF, clock64() - dbg_t0) | (tiled ? 0u : 0x80000000u);
 #ifdef B200ICP_DBG_COUNT
@@ -484,13 +459,12 @@ struct SearchSmem
 // search (rows of job j start at J.pair_base); used when the job says its rows
 // are valid (JobDev::rows_valid, set by the solver after a matcher run).
 #ifndef B200ICP_SEARCH_MINB
-#define B200ICP_SEARCH_MINB 1
+#define B200ICP_SEARCH_MINB 4
 #endif
 template <int K, class Epi>
 __global__ void __launch_bounds__(kChunk, B200ICP_SEARCH_MINB)
     search_tile_kernel(const CloudView* __restrict__ clouds, JobDev* __restrict__ jobs, IcpDevParams P,
-                       float cap_d2, int gate, const uint32_t* seed_nn, uint32_t seed_k, uint2* heavy,
-                       uint32_t budget, Epi epi)
+                       float cap_d2, int gate, const uint32_t* seed_nn, uint32_t seed_k, Epi epi)
 {
     JobDev& J = jobs[blockIdx.y];
     if (gate == 1 && (J.status != 0 || !matcher_active(P, J.iter))) return;  // matcher: running jobs only
@@ -506,57 +480,10 @@ __global__ void __launch_bounds__(kChunk, B200ICP_SEARCH_MINB)
     const uint32_t n_items = (sm.grid.n_valid > 0) ? sm.n_items : 0u;
     SeedRows       seed = {nullptr, seed_k};
     if (seed_nn && J.rows_valid) seed.rows = seed_nn + (size_t)J.pair_base * seed_k;
-    const HeavyQueue hq = {&J.heavy_count, heavy ? heavy + J.pair_base : nullptr, heavy ? budget : 0xFFFFFFFFu};
-    for_each_item<K>(sm.tile[tid >> 5], cvL, cvG, sm.grid, sm.Rt, n_items, &J.next_item, cap_d2, seed, hq,
+    for_each_item<K>(sm.tile[tid >> 5], cvL, cvG, sm.grid, sm.Rt, n_items, &J.next_item, cap_d2, seed,
                      [&](bool has, uint32_t pos, uint32_t orig, uint64_t (&key)[K], uint64_t sent) {
                          epi(J, cvG, has, pos, orig, key, sent);
                      });
-}
-
-// Second pass of a search: the queries of the heavy list, eight lanes each
-// (coop_search.cuh).  Same gates and the same epilogue as the first pass; the
-// list was filled by search_tile_kernel of the same launch pair.
-struct HeavySmem
-{
-    CoopWarpSmem warp[kChunk / 32];
-    GridDev      grid;
-    double       Rt[12];
-};
-
-template <int K, class Epi>
-__global__ void __launch_bounds__(kChunk)
-    search_heavy_kernel(const CloudView* __restrict__ clouds, JobDev* __restrict__ jobs, IcpDevParams P,
-                        int gate, const uint2* __restrict__ heavy, Epi epi)
-{
-    JobDev& J = jobs[blockIdx.y];
-    if (gate == 1 && (J.status != 0 || !matcher_active(P, J.iter))) return;
-    if (gate == 2 && (J.status == 0 || J.evaluated != 0)) return;
-    const uint32_t n_heavy = J.heavy_count;
-    if (n_heavy == 0) return;
-    const CloudView cvL = clouds[J.to_cloud];
-    const CloudView cvG = clouds[J.from_cloud];
-    __shared__ HeavySmem sm;
-    const int tid = threadIdx.x, lane = tid & 31;
-    if (tid < 12) sm.Rt[tid] = (tid < 9) ? J.R[tid] : J.t[tid - 9];
-    if (tid == 12) sm.grid = *cvG.grid;
-    __syncthreads();
-    const uint2*   list = heavy + J.pair_base;
-    const uint32_t n_tasks = (n_heavy + kSubPerWarp - 1) / kSubPerWarp;
-    for (uint32_t task = item_warp_id(); task < n_tasks; task += item_warp_count())
-    {
-        const uint32_t h = task * kSubPerWarp + (uint32_t)(lane / kSub);
-        const bool     active = h < n_heavy;
-        uint2          e = make_uint2(0u, 0u);
-        if (active) e = list[h];
-        float4 pl = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active) pl = __ldg(cvL.pts + e.x);
-        double gx, gy, gz;
-        transform_point(sm.Rt, pl, gx, gy, gz);
-        const float cap = __uint_as_float(e.y);
-        uint64_t    key[K];
-        coop_knn<K>(sm.warp[tid >> 5], cvG, sm.grid, active, (float)gx, (float)gy, (float)gz, cap, key);
-        epi(J, cvG, active && (lane % kSub) == 0, e.x, __float_as_uint(pl.w), key, sentinel_key(cap));
-    }
 }
 
 // ================================================================= fit stage
@@ -594,47 +521,167 @@ __device__ __forceinline__ void accumulate_moments(double* st, bool paired, cons
     }
 }
 
-// CTA partial: the four warps' tiles added in a fixed order. `wbuf` is 4 x 192
-// doubles of shared memory nobody else uses any more.
-__device__ __forceinline__ void write_cta_partial(double* wbuf, const double (&c00)[2],
-                                                  const double (&c01)[2], const double (&c11)[2],
-                                                  double* __restrict__ partial)
+// ---- moments: chunk partials and their fixed reduction tree ------------------
+// The local cloud's items are taken in CHUNKS of `chunk_items` consecutive items.
+// One warp accumulates a chunk (DMMA accumulators in registers) and stores its
+// 192 doubles as partial[chunk]; the partials of kFitGroup consecutive chunks
+// are summed, in chunk order, into gpartial[group]; the group partials are summed
+// in group order into the job's moment matrix.  The tree is defined over the
+// DATA (positions in the local cloud), not over who executes what: any launch
+// shape, any scheduling -- and any split of the chunks over several GPUs --
+// gives the same bits.  Who runs a reduction step is decided by arrival
+// counters: the last warp to deliver a partial of a group reduces the group, the
+// last group reducer reduces the job and -- tail_mode 1 -- runs the solver on the
+// result right away (no separate launch, no second pass over the partials).
+constexpr int kFitGroup = 32;  // chunk partials per first-level sum
+
+struct FitBuffers
 {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __syncthreads();
+    double*   partials;   // [job chunk base + chunk][192], fragment layout (see frag_slots)
+    double*   gpartials;  // [job group base + group][192]
+    uint32_t* tickets;    // [job group base + group] arrival counters; zero between launches
+};
+
+// Scratch of the solver (one warp), one per CTA: only one warp of a job's grid row ever gets there.
+struct SolveSmem
+{
+    double S[kNumMoments];
+    double A[144];
+    double G0[12];   // sum a r0
+    double T0[12];   // theta0 layout: [R_i0 R_i1 R_i2 t_i] x 3
+    double R[9], t[3];
+    double X[12], G12[12], Jm[72], B[72], H[36], g[6];
+    int    stop;
+};
+
+// the six elements of S a lane holds after the DMMAs: rows r = lane / 4, columns 2 (lane % 4) and + 1 of each tile
+__device__ __forceinline__ void frag_slots(int lane, int (&idx)[6])
+{
+    const int r = lane >> 2, c = 2 * (lane & 3);
+    idx[0] = r * 8 + c, idx[1] = idx[0] + 1;
+    idx[2] = 64 + r * 8 + c, idx[3] = idx[2] + 1;
+    idx[4] = 128 + r * 8 + c, idx[5] = idx[4] + 1;
+}
+
+// Sum of `count` consecutive 192-double records, this lane's six slots, in a
+// FIXED order: four interleaved running sums over the records in sequence, then
+// a balanced tree.  L2 loads (the records were written by other SMs in this launch).
+__device__ __forceinline__ void sum_records(const double* base, uint32_t count, const int (&idx)[6], double (&v)[6])
+{
+    double   a[4][6];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int i = 0; i < 6; i++) a[u][i] = 0.0;
+    uint32_t c = 0;
+    for (; c + 4 <= count; c += 4)
     {
-        const int r = lane >> 2, c = 2 * (lane & 3);
-        double*   w = wbuf + warp * kNumMoments;
-        w[r * 8 + c] = c00[0], w[r * 8 + c + 1] = c00[1];
-        w[64 + r * 8 + c] = c01[0], w[64 + r * 8 + c + 1] = c01[1];
-        w[128 + r * 8 + c] = c11[0], w[128 + r * 8 + c + 1] = c11[1];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int i = 0; i < 6; i++) a[u][i] += __ldcg(base + (size_t)(c + u) * kNumMoments + idx[i]);
     }
-    __syncthreads();
-    for (int i = tid; i < kNumMoments; i += kChunk)
-        partial[i] = (wbuf[i] + wbuf[kNumMoments + i]) + (wbuf[2 * kNumMoments + i] + wbuf[3 * kNumMoments + i]);
+    for (uint32_t u = 0; c < count; c++, u++)
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+        {   // the up-to-three records left go to the running sums 0, 1, 2
+            const double x = __ldcg(base + (size_t)c * kNumMoments + idx[i]);
+            if (u == 0) a[0][i] += x;
+            else if (u == 1) a[1][i] += x;
+            else a[2][i] += x;
+        }
+#pragma unroll
+    for (int i = 0; i < 6; i++) v[i] = (a[0][i] + a[1][i]) + (a[2][i] + a[3][i]);
+}
+
+// Called by the whole warp that has just accumulated chunk `chunk` (of n_chunks)
+// of job J.  Returns true on the ONE warp of the job that then holds the fully
+// reduced moments: in sS[192] (shared) and in J.M.
+__device__ __forceinline__ bool deliver_chunk(JobDev& J, uint32_t chunk, uint32_t n_chunks, const double (&c00)[2],
+                                              const double (&c01)[2], const double (&c11)[2],
+                                              const FitBuffers& fb, double* sS)
+{
+    const int lane = threadIdx.x & 31;
+    int       idx[6];
+    frag_slots(lane, idx);
+    double* pp = fb.partials + (size_t)(J.chunk_base + chunk) * kNumMoments;
+    pp[idx[0]] = c00[0], pp[idx[1]] = c00[1], pp[idx[2]] = c01[0];
+    pp[idx[3]] = c01[1], pp[idx[4]] = c11[0], pp[idx[5]] = c11[1];
+    __threadfence();
+    __syncwarp();
+    const uint32_t g = chunk / kFitGroup, n_groups = (n_chunks + kFitGroup - 1) / kFitGroup;
+    const uint32_t in_group = min((uint32_t)kFitGroup, n_chunks - g * kFitGroup);
+    uint32_t       t = 0;
+    if (lane == 0) t = atomicAdd(fb.tickets + J.group_base + g, 1u);
+    t = __shfl_sync(0xFFFFFFFFu, t, 0);
+    if (t != in_group - 1) return false;
+    // last of its group: first-level sum
+    __threadfence();
+    double v[6];
+    sum_records(fb.partials + (size_t)(J.chunk_base + g * kFitGroup) * kNumMoments, in_group, idx, v);
+    double* gp = fb.gpartials + (size_t)(J.group_base + g) * kNumMoments;
+#pragma unroll
+    for (int i = 0; i < 6; i++) gp[idx[i]] = v[i];
+    if (lane == 0) fb.tickets[J.group_base + g] = 0;  // ready for the next launch
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) t = atomicAdd(&J.groups_done, 1u);
+    t = __shfl_sync(0xFFFFFFFFu, t, 0);
+    if (t != n_groups - 1) return false;
+    // last group: the job's moments
+    if (lane == 0) J.groups_done = 0;
+    __threadfence();
+    const long long t0 = clock64();
+    sum_records(fb.gpartials + (size_t)J.group_base * kNumMoments, n_groups, idx, v);
+    if (lane == 0) J.dbg_tail[0] = (uint32_t)(clock64() - t0);
+#pragma unroll
+    for (int i = 0; i < 6; i++) sS[idx[i]] = v[i], J.M[idx[i]] = v[i];
+    __syncwarp();
+    return true;
 }
 
 struct FitSmem
 {
-    double   stage[kChunk / 32][16 * kStageStride];  // half a warp of e-vectors per round; later the CTA partial
-    double   Rt[12];
-    uint32_t n_items;
+    double    stage[kChunk / 32][16 * kStageStride];  // half a warp of e-vectors per round
+    SolveSmem solve;
+    double    Rt[12];
+    uint32_t  n_items;
 };
-static_assert(16 * kStageStride >= kNumMoments, "the stage buffers double as the CTA partial");
+
+__device__ void solve_job_warp(JobDev& J, SolveSmem& ss, const IcpDevParams& P, uint32_t* n_active);
+
+// what a fit kernel does once a warp holds the job's reduced moments (or there is nothing to reduce)
+__device__ __forceinline__ void fit_job_tail(JobDev& J, FitSmem& sm, int tail_mode, const IcpDevParams& P,
+                                             uint32_t* n_active)
+{
+    if (tail_mode == 1) solve_job_warp(J, sm.solve, P, n_active);
+}
+
+// a job whose matcher does not run at this iteration (or that has nothing to match): zero moments, then the tail
+__device__ __forceinline__ void fit_job_without_chunks(JobDev& J, FitSmem& sm, int tail_mode, const IcpDevParams& P,
+                                                       uint32_t* n_active)
+{
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < kNumMoments; i += 32) sm.solve.S[i] = 0.0, J.M[i] = 0.0;
+    __syncwarp();
+    fit_job_tail(J, sm, tail_mode, P, n_active);
+}
 
 // Matcher_Point2Plane after the search (rows H, J) + the per-pairing part of
 // optimal_tf_gauss_newton (rows K, L).  One thread per local point, in the
-// cloud's sorted order; warp w takes the items w, w + W, ... (static: the
-// summation order of the moments never depends on scheduling).
+// cloud's sorted order; a warp takes whole chunks of `chunk_items` items (see
+// "chunk partials" above: the summation order of the moments never depends on
+// scheduling or on the launch shape).  The warp that completes the job's
+// reduction runs the solver (tail_mode 1) or leaves the moments in J.M (0).
 // grid = (CTAs per job, jobs).  nn = [job base + sorted position][K].
 template <int K, bool WRITE>
 __global__ void __launch_bounds__(kChunk, 4)
-    fit_plane_kernel(const CloudView* __restrict__ clouds, const JobDev* __restrict__ jobs,
-                     const uint32_t* __restrict__ nn, double* __restrict__ partials, IcpDevParams P,
-                     MatchOut out, PairRec* __restrict__ pairs)
+    fit_plane_kernel(const CloudView* __restrict__ clouds, JobDev* __restrict__ jobs,
+                     const uint32_t* __restrict__ nn, FitBuffers fb, uint32_t chunk_items, int tail_mode,
+                     IcpDevParams P, MatchOut out, PairRec* __restrict__ pairs, uint32_t* __restrict__ n_active)
 {
     const uint32_t job = blockIdx.y;
-    const JobDev&  J = jobs[job];
+    JobDev&        J = jobs[job];
     if (J.status != 0) return;
     const CloudView cvL = clouds[J.to_cloud];
     const CloudView cvG = clouds[J.from_cloud];
@@ -647,11 +694,22 @@ __global__ void __launch_bounds__(kChunk, 4)
     if (tid == 32) sm.n_items = (cvG.grid->n_valid > 0) ? cvL.grid->n_items : 0u;
     __syncthreads();
     const uint32_t n_items = matcher_active(P, J.iter) ? sm.n_items : 0u;
-    double         c00[2] = {0, 0}, c01[2] = {0, 0}, c11[2] = {0, 0};
+    const uint32_t n_chunks = (n_items + chunk_items - 1) / chunk_items;
     double*        st = sm.stage[warp];
-
-    for (uint32_t item = item_warp_id(); item < n_items; item += item_warp_count())
+    if (n_chunks == 0)
     {
+        if (blockIdx.x == 0 && warp == 0) fit_job_without_chunks(J, sm, tail_mode, P, n_active);
+        return;
+    }
+
+    // the delivery that completes a job is always some warp's LAST chunk: the tail runs after the loop, when
+    // nothing of the loop is live any more
+    bool completes_job = false;
+    for (uint32_t chunk = item_warp_id(); chunk < n_chunks; chunk += item_warp_count())
+    {
+      double c00[2] = {0, 0}, c01[2] = {0, 0}, c11[2] = {0, 0};
+      for (uint32_t item = chunk * chunk_items; item < min(n_items, (chunk + 1) * chunk_items); item++)
+      {
         const uint32_t first = __ldg(cvL.item_first + item);
         const uint32_t cnt = __ldg(cvL.item_first + item + 1) - first;
         const bool     has = (uint32_t)lane < cnt;
@@ -771,10 +829,10 @@ __global__ void __launch_bounds__(kChunk, 4)
         }
         e[12] = r0, e[13] = f1, e[14] = 0.0, e[15] = 0.0;
         accumulate_moments(st, paired, e, c00, c01, c11);
+      }
+      completes_job = deliver_chunk(J, chunk, n_chunks, c00, c01, c11, fb, sm.solve.S);
     }
-
-    write_cta_partial(&sm.stage[0][0], c00, c01, c11,
-                      partials + ((size_t)job * gridDim.x + blockIdx.x) * kNumMoments);
+    if (completes_job) fit_job_tail(J, sm, tail_mode, P, n_active);
 }
 
 // Matcher_Points_DistanceThreshold as the ICP matcher: 1-NN with d2 < thr^2
@@ -785,12 +843,12 @@ __global__ void __launch_bounds__(kChunk, 4)
 // and the pairing count (S[3][3]).  nn = [job base + sorted position][1].
 template <bool WRITE>
 __global__ void __launch_bounds__(kChunk)
-    fit_p2p_kernel(const CloudView* __restrict__ clouds, const JobDev* __restrict__ jobs,
-                   const uint32_t* __restrict__ nn, double* __restrict__ partials, IcpDevParams P,
-                   MatchOut out, PairRec* __restrict__ pairs)
+    fit_p2p_kernel(const CloudView* __restrict__ clouds, JobDev* __restrict__ jobs,
+                   const uint32_t* __restrict__ nn, FitBuffers fb, uint32_t chunk_items, int tail_mode,
+                   IcpDevParams P, MatchOut out, PairRec* __restrict__ pairs, uint32_t* __restrict__ n_active)
 {
     const uint32_t job = blockIdx.y;
-    const JobDev&  J = jobs[job];
+    JobDev&        J = jobs[job];
     if (J.status != 0) return;
     const CloudView cvL = clouds[J.to_cloud];
     const CloudView cvG = clouds[J.from_cloud];
@@ -803,11 +861,22 @@ __global__ void __launch_bounds__(kChunk)
     if (tid == 32) sm.n_items = (cvG.grid->n_valid > 0) ? cvL.grid->n_items : 0u;
     __syncthreads();
     const uint32_t n_items = matcher_active(P, J.iter) ? sm.n_items : 0u;
-    double         c00[2] = {0, 0}, c01[2] = {0, 0}, c11[2] = {0, 0};
+    const uint32_t n_chunks = (n_items + chunk_items - 1) / chunk_items;
     double*        st = sm.stage[warp];
-
-    for (uint32_t item = item_warp_id(); item < n_items; item += item_warp_count())
+    if (n_chunks == 0)
     {
+        if (blockIdx.x == 0 && warp == 0) fit_job_without_chunks(J, sm, tail_mode, P, n_active);
+        return;
+    }
+
+    // the delivery that completes a job is always some warp's LAST chunk: the tail runs after the loop, when
+    // nothing of the loop is live any more
+    bool completes_job = false;
+    for (uint32_t chunk = item_warp_id(); chunk < n_chunks; chunk += item_warp_count())
+    {
+      double c00[2] = {0, 0}, c01[2] = {0, 0}, c11[2] = {0, 0};
+      for (uint32_t item = chunk * chunk_items; item < min(n_items, (chunk + 1) * chunk_items); item++)
+      {
         const uint32_t first = __ldg(cvL.item_first + item);
         const uint32_t cnt = __ldg(cvL.item_first + item + 1) - first;
         const bool     has = (uint32_t)lane < cnt;
@@ -854,9 +923,10 @@ __global__ void __launch_bounds__(kChunk)
 #pragma unroll
         for (int i = 7; i < 16; i++) e[i] = 0.0;
         accumulate_moments(st, paired, e, c00, c01, c11);
+      }
+      completes_job = deliver_chunk(J, chunk, n_chunks, c00, c01, c11, fb, sm.solve.S);
     }
-    write_cta_partial(&sm.stage[0][0], c00, c01, c11,
-                      partials + ((size_t)job * gridDim.x + blockIdx.x) * kNumMoments);
+    if (completes_job) fit_job_tail(J, sm, tail_mode, P, n_active);
 }
 
 // ------------------------------------------------------------------- solver
@@ -897,76 +967,22 @@ __device__ void finish_outer_iteration(JobDev& J, const Pose& Tn, uint32_t npair
     }
 }
 
-// Fixed-order reduction of a job's per-CTA moment partials by a block of
-// kSolveThreads threads: group g takes the partials c = g (mod 4) with four
-// interleaved accumulators, then the group sums are added as a balanced tree --
-// the order never depends on scheduling.  Result in sS[192] (and J.M).
-// One CTA per job. Warp 0 runs the Gauss-Newton inner loop on the moments.
-constexpr int kSolveGroups = 4;  // 4 x 192 threads share the partials reduction
-constexpr int kSolveThreads = kSolveGroups * kNumMoments;
-
-__device__ __forceinline__ void reduce_moment_partials(const double* __restrict__ partials, uint32_t job,
-                                                       uint32_t n_partials, double* sS,
-                                                       double (*sPart)[kNumMoments])
+// optimal_tf_gauss_newton on the reduced moments (A.6) + the end of the outer
+// iteration (A.7), by ONE warp: the one that completed the job's reduction in the
+// fit kernel.  ss.S holds the moments.
+__device__ void solve_job_warp(JobDev& J, SolveSmem& ss, const IcpDevParams& P, uint32_t* n_active)
 {
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    if (lane == 0)
     {
-        const int     grp = tid / kNumMoments, comp = tid % kNumMoments;
-        const double* p = partials + (size_t)job * n_partials * kNumMoments + comp;
-        double        a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-        uint32_t      c = grp;
-        // eight loads in flight per thread: the partials sit in L2, the loop
-        // is latency bound
-        for (; c + 7 * kSolveGroups < n_partials; c += 8 * kSolveGroups)
-        {
-            const double v0 = p[(size_t)c * kNumMoments];
-            const double v1 = p[(size_t)(c + kSolveGroups) * kNumMoments];
-            const double v2 = p[(size_t)(c + 2 * kSolveGroups) * kNumMoments];
-            const double v3 = p[(size_t)(c + 3 * kSolveGroups) * kNumMoments];
-            const double v4 = p[(size_t)(c + 4 * kSolveGroups) * kNumMoments];
-            const double v5 = p[(size_t)(c + 5 * kSolveGroups) * kNumMoments];
-            const double v6 = p[(size_t)(c + 6 * kSolveGroups) * kNumMoments];
-            const double v7 = p[(size_t)(c + 7 * kSolveGroups) * kNumMoments];
-            a0 += v0, a1 += v1, a2 += v2, a3 += v3;
-            a0 += v4, a1 += v5, a2 += v6, a3 += v7;
-        }
-        for (; c < n_partials; c += kSolveGroups) a0 += p[(size_t)c * kNumMoments];
-        sPart[grp][comp] = (a0 + a1) + (a2 + a3);
+        J.next_item = 0;                                   // the next search draws items from 0 again
+        if (matcher_active(P, J.iter)) J.rows_valid = 1;   // this iteration's search wrote the neighbour rows
     }
-    __syncthreads();
-    if (tid < kNumMoments)
-        sS[tid] = (sPart[0][tid] + sPart[1][tid]) + (sPart[2][tid] + sPart[3][tid]);
-    __syncthreads();
-}
-
-__global__ void __launch_bounds__(kSolveThreads)
-    solve_kernel(const CloudView* __restrict__ clouds, JobDev* __restrict__ jobs,
-                 const double* __restrict__ partials, uint32_t n_partials, IcpDevParams P,
-                 uint32_t* __restrict__ n_active)
-{
-    const uint32_t job = blockIdx.x;
-    JobDev&        J = jobs[job];
-    if (threadIdx.x == 0) J.next_item = 0, J.heavy_count = 0;  // the next search starts from scratch
-    if (J.status != 0) return;
-    if (threadIdx.x == 0 && matcher_active(P, J.iter)) J.rows_valid = 1;  // this iteration's search wrote them
-    const int tid = threadIdx.x, lane = tid & 31;
-
-    __shared__ double sS[kNumMoments];
-    __shared__ double sPart[kSolveGroups][kNumMoments];
-    __shared__ double sA[144];
-    __shared__ double sG0[12];   // sum a r0
-    __shared__ double sT0[12];   // theta0 layout: [R_i0 R_i1 R_i2 t_i] x 3
-    __shared__ double sR[9], st[3];
-    __shared__ double sX[12], sG12[12], sJ[72], sB[72], sH[36], sg[6];
-    __shared__ int    sStop;
-
-    reduce_moment_partials(partials, job, n_partials, sS, sPart);
-    if (tid < kNumMoments) J.M[tid] = sS[tid];
     const bool     p2p = (P.matcher_kind == B200ICP_MATCHER_POINTS_DISTANCE);
-    const uint32_t npair = (uint32_t)(pairing_count(sS, p2p) + 0.5);
+    const uint32_t npair = (uint32_t)(pairing_count(ss.S, p2p) + 0.5);
     if (npair == 0)
     {
-        if (tid == 0)
+        if (lane == 0)
         {
             J.n_pairings = 0;
             J.status = 1;
@@ -975,22 +991,21 @@ __global__ void __launch_bounds__(kSolveThreads)
         }
         return;
     }
-    for (int e = tid; e < 144; e += blockDim.x) sA[e] = normal_matrix_at(sS, p2p, e / 12, e % 12);
-    if (tid < 12)
+    for (int e = lane; e < 144; e += 32) ss.A[e] = normal_matrix_at(ss.S, p2p, e / 12, e % 12);
+    if (lane < 12)
     {
-        const int    i = tid >> 2, j = tid & 3;
+        const int    i = lane >> 2, j = lane & 3;
         const double v = (j < 3) ? J.R[i * 3 + j] : J.t[i];
-        sT0[tid] = v;
-        sG0[tid] = p2p ? moment_at(sS, j, 4 + i) : moment_at(sS, tid, 12);
+        ss.T0[lane] = v;
+        ss.G0[lane] = p2p ? moment_at(ss.S, j, 4 + i) : moment_at(ss.S, lane, 12);
         if (j < 3)
-            sR[i * 3 + j] = v;
+            ss.R[i * 3 + j] = v;
         else
-            st[i] = v;
+            ss.t[i] = v;
     }
-    __syncthreads();
-    if (tid >= 32) return;
+    __syncwarp();
 
-    // ---- Gauss-Newton on the moments (A.6), warp 0 -------------------------
+    const long long t_gn = clock64();
     uint32_t inner = 0;
     for (uint32_t iter = 0; iter < P.solver_max_iterations; iter++)
     {
@@ -998,7 +1013,7 @@ __global__ void __launch_bounds__(kSolveThreads)
         if (lane < 12)
         {
             const int i = lane >> 2, j = lane & 3;
-            sX[lane] = ((j < 3) ? sR[i * 3 + j] : st[i]) - sT0[lane];
+            ss.X[lane] = ((j < 3) ? ss.R[i * 3 + j] : ss.t[i]) - ss.T0[lane];
         }
         // J = d theta / d eps (12 x 6): columns v0..2 then w0..2
         for (int e = lane; e < 72; e += 32)
@@ -1006,28 +1021,28 @@ __global__ void __launch_bounds__(kSolveThreads)
             const int a = e / 6, c = e % 6, i = a >> 2, l = a & 3;
             double    v = 0.0;
             if (c < 3)
-                v = (l == 3) ? sR[i * 3 + c] : 0.0;
+                v = (l == 3) ? ss.R[i * 3 + c] : 0.0;
             else if (l < 3)
             {
                 const int j = c - 3;
                 // (R [e_j]x)[i][l]
                 if (j == 0)
-                    v = (l == 1) ? sR[i * 3 + 2] : (l == 2 ? -sR[i * 3 + 1] : 0.0);
+                    v = (l == 1) ? ss.R[i * 3 + 2] : (l == 2 ? -ss.R[i * 3 + 1] : 0.0);
                 else if (j == 1)
-                    v = (l == 0) ? -sR[i * 3 + 2] : (l == 2 ? sR[i * 3 + 0] : 0.0);
+                    v = (l == 0) ? -ss.R[i * 3 + 2] : (l == 2 ? ss.R[i * 3 + 0] : 0.0);
                 else
-                    v = (l == 0) ? sR[i * 3 + 1] : (l == 1 ? -sR[i * 3 + 0] : 0.0);
+                    v = (l == 0) ? ss.R[i * 3 + 1] : (l == 1 ? -ss.R[i * 3 + 0] : 0.0);
             }
-            sJ[e] = v;
+            ss.Jm[e] = v;
         }
         __syncwarp();
         // g12 = s + A x
         if (lane < 12)
         {
-            double acc = sG0[lane];
+            double acc = ss.G0[lane];
 #pragma unroll
-            for (int b = 0; b < 12; b++) acc += sA[lane * 12 + b] * sX[b];
-            sG12[lane] = acc;
+            for (int b = 0; b < 12; b++) acc += ss.A[lane * 12 + b] * ss.X[b];
+            ss.G12[lane] = acc;
         }
         // B = A J
         for (int e = lane; e < 72; e += 32)
@@ -1035,8 +1050,8 @@ __global__ void __launch_bounds__(kSolveThreads)
             const int a = e / 6, c = e % 6;
             double    acc = 0;
 #pragma unroll
-            for (int b = 0; b < 12; b++) acc += sA[a * 12 + b] * sJ[b * 6 + c];
-            sB[e] = acc;
+            for (int b = 0; b < 12; b++) acc += ss.A[a * 12 + b] * ss.Jm[b * 6 + c];
+            ss.B[e] = acc;
         }
         __syncwarp();
         // H = J^T B, g = J^T g12
@@ -1045,44 +1060,46 @@ __global__ void __launch_bounds__(kSolveThreads)
             const int r = e / 6, c = e % 6;
             double    acc = 0;
 #pragma unroll
-            for (int a = 0; a < 12; a++) acc += sJ[a * 6 + r] * sB[a * 6 + c];
-            sH[e] = acc;
+            for (int a = 0; a < 12; a++) acc += ss.Jm[a * 6 + r] * ss.B[a * 6 + c];
+            ss.H[e] = acc;
         }
         if (lane < 6)
         {
             double acc = 0;
 #pragma unroll
-            for (int a = 0; a < 12; a++) acc += sJ[a * 6 + lane] * sG12[a];
-            sg[lane] = acc;
+            for (int a = 0; a < 12; a++) acc += ss.Jm[a * 6 + lane] * ss.G12[a];
+            ss.g[lane] = acc;
         }
         __syncwarp();
         if (lane == 0)
         {
             double Hm[36], mg[6], delta[6];
-            for (int i = 0; i < 36; i++) Hm[i] = 0.5 * (sH[i] + sH[(i % 6) * 6 + i / 6]);
-            for (int i = 0; i < 6; i++) mg[i] = -sg[i];
+            for (int i = 0; i < 36; i++) Hm[i] = 0.5 * (ss.H[i] + ss.H[(i % 6) * 6 + i / 6]);
+            for (int i = 0; i < 6; i++) mg[i] = -ss.g[i];
             solve6_spd(Hm, mg, delta);
             Pose T, dT, Tn;
-            for (int i = 0; i < 9; i++) T.R[i] = sR[i];
-            for (int i = 0; i < 3; i++) T.t[i] = st[i];
+            for (int i = 0; i < 9; i++) T.R[i] = ss.R[i];
+            for (int i = 0; i < 3; i++) T.t[i] = ss.t[i];
             se3_exp(delta, dT);
             pose_compose(T, dT, Tn);
-            for (int i = 0; i < 9; i++) sR[i] = Tn.R[i];
-            for (int i = 0; i < 3; i++) st[i] = Tn.t[i];
+            for (int i = 0; i < 9; i++) ss.R[i] = Tn.R[i];
+            for (int i = 0; i < 3; i++) ss.t[i] = Tn.t[i];
             double nd = 0;
             for (int i = 0; i < 6; i++) nd += delta[i] * delta[i];
-            sStop = (sqrt(nd) < P.gn_min_delta) ? 1 : 0;
+            ss.stop = (sqrt(nd) < P.gn_min_delta) ? 1 : 0;
         }
         __syncwarp();
         inner++;
-        if (sStop) break;
+        if (ss.stop) break;
     }
     if (lane == 0)
     {
+        const long long t_fin = clock64();
         Pose Tn;
-        for (int i = 0; i < 9; i++) Tn.R[i] = sR[i];
-        for (int i = 0; i < 3; i++) Tn.t[i] = st[i];
+        for (int i = 0; i < 9; i++) Tn.R[i] = ss.R[i];
+        for (int i = 0; i < 3; i++) Tn.t[i] = ss.t[i];
         finish_outer_iteration(J, Tn, npair, inner, P, n_active);
+        J.dbg_tail[1] = (uint32_t)(t_fin - t_gn), J.dbg_tail[2] = (uint32_t)(clock64() - t_fin), J.dbg_tail[3] = inner;
     }
 }
 
@@ -1196,24 +1213,20 @@ __global__ void __launch_bounds__(kHornThreads)
     }
 }
 
-__global__ void __launch_bounds__(kSolveThreads)
-    horn_solve_kernel(JobDev* __restrict__ jobs, const double* __restrict__ partials,
-                      uint32_t n_partials, const double* __restrict__ part0,
+constexpr int kHornSolveThreads = 32;
+__global__ void __launch_bounds__(kHornSolveThreads)
+    horn_solve_kernel(JobDev* __restrict__ jobs, const double* __restrict__ part0,
                       const double* __restrict__ part1, uint32_t n_hpart, IcpDevParams P,
                       uint32_t* __restrict__ n_active)
 {
     const uint32_t job = blockIdx.x;
     JobDev&        J = jobs[job];
-    if (threadIdx.x == 0) J.next_item = 0, J.heavy_count = 0;  // the next search starts from scratch
+    if (threadIdx.x == 0) J.next_item = 0;  // the next search draws items from 0 again
     if (J.status != 0) return;
     if (threadIdx.x == 0 && matcher_active(P, J.iter)) J.rows_valid = 1;  // this iteration's search wrote them
     const int tid = threadIdx.x;
-    __shared__ double sS[kNumMoments];
-    __shared__ double sPart[kSolveGroups][kNumMoments];
     __shared__ double sH[kHornVals];
-    // the matcher's moments are only needed for the covariance at the end
-    reduce_moment_partials(partials, job, n_partials, sS, sPart);
-    if (tid < kNumMoments) J.M[tid] = sS[tid];
+    // the matcher's moments (needed for the covariance at the end) are already in J.M: the fit kernel's tail
     if (tid < 10)
     {
         double        v = 0;
@@ -1382,8 +1395,6 @@ struct SearchConfig
     int  wpi = 0;  // 0 = automatic
     bool graphs = true;  // B200ICP_GRAPH=0: no CUDA-graph replay of single registrations
     bool seeds = true;   // B200ICP_SEED=0: searches never take their bound from the previous neighbour rows
-    uint32_t budget = 96;  // B200ICP_BUDGET: candidates a lane scans before its query goes to the cooperative
-                           // pass (0 = no limit, no second pass)
 };
 static const SearchConfig& search_config()
 {
@@ -1393,20 +1404,15 @@ static const SearchConfig& search_config()
         if (const char* w = getenv("B200ICP_WPI")) c.wpi = atoi(w);
         if (const char* g = getenv("B200ICP_GRAPH")) c.graphs = atoi(g) != 0;
         if (const char* g = getenv("B200ICP_SEED")) c.seeds = atoi(g) != 0;
-        if (const char* g = getenv("B200ICP_BUDGET")) c.budget = atoi(g) > 0 ? (uint32_t)atoi(g) : 0xFFFFFFFFu;
         return c;
     }();
     return cfg;
 }
 
-// CTAs per job of the FIT stage: every warp walks the items w, w + W, ... of
-// the local cloud.  Enough warps to fill the machine for one job, fewer per
-// job when many jobs share a launch (the partials buffer is G x 192 doubles
-// per job), and a warp count that gives every warp the same number of items.
-static uint32_t fit_ctas_per_job(const ::b200icp* ctx, size_t max_points, size_t njobs)
+// CTAs per job of the FIT stage: one warp per chunk up to a full resident wave for a single job, fewer per job
+// when many jobs share a launch.  Any value gives the same results (chunk partials).
+static uint32_t fit_ctas_per_job(const ::b200icp* ctx, size_t max_points, size_t njobs, uint32_t chunk_items)
 {
-    // CTAs of the fit kernel resident on one SM (registers): one full wave for
-    // a single job, never a ragged second one
     static int resident = 0;
     if (resident == 0)
     {
@@ -1417,21 +1423,18 @@ static uint32_t fit_ctas_per_job(const ::b200icp* ctx, size_t max_points, size_t
         resident = occ;
     }
     const size_t items = std::max<size_t>(1, (max_points + kItem - 1) / kItem);
+    const size_t chunks = (items + chunk_items - 1) / chunk_items;
     const size_t warps_per_cta = kChunk / 32;
-    const size_t wave_warps = (size_t)ctx->sm_count * resident * warps_per_cta;
-    size_t       max_warps = std::max<size_t>(warps_per_cta * 2, (2 * wave_warps + njobs - 1) / njobs);
-    max_warps = std::min<size_t>(max_warps, wave_warps);
-    const size_t per_warp = (items + max_warps - 1) / max_warps;
-    const size_t warps = (items + per_warp - 1) / per_warp;
-    return (uint32_t)std::max<size_t>(1, (warps + warps_per_cta - 1) / warps_per_cta);
+    const size_t wave = (size_t)ctx->sm_count * resident;
+    const size_t cap = std::max<size_t>(2, (2 * wave + njobs - 1) / njobs);
+    return (uint32_t)std::max<size_t>(1, std::min({(chunks + warps_per_cta - 1) / warps_per_cta, cap, wave}));
 }
 
 // search stage over a table of jobs: grid = (items of the largest local cloud, jobs)
 template <int K, class Epi>
 static void launch_search_k(const ::b200icp* ctx, Workspace* ws, size_t max_points, size_t njobs,
                             const CloudView* d_clouds, JobDev* d_jobs, const IcpDevParams& D, float cap_d2,
-                            int gate, const Epi& epi, uint2* d_heavy, const uint32_t* seed_nn = nullptr,
-                            uint32_t seed_k = 0)
+                            int gate, const Epi& epi, const uint32_t* seed_nn = nullptr, uint32_t seed_k = 0)
 {
     cudaStream_t        s = ws->stream;
     const SearchConfig& cfg = search_config();
@@ -1452,17 +1455,8 @@ static void launch_search_k(const ::b200icp* ctx, Workspace* ws, size_t max_poin
         const size_t   wave = (size_t)ctx->sm_count * resident;
         const size_t   cap = std::max<size_t>(4, (2 * wave + njobs - 1) / njobs);
         const uint32_t G = (uint32_t)std::max<size_t>(1, std::min({(items + warps - 1) / warps, cap, wave}));
-        const uint32_t budget = cfg.budget;
-        uint2*         heavy = (budget != 0xFFFFFFFFu) ? d_heavy : nullptr;
         search_tile_kernel<K, Epi><<<dim3(G, (unsigned)njobs), kChunk, 0, s>>>(d_clouds, d_jobs, D, cap_d2, gate,
-                                                                              seed_nn, seed_k, heavy, budget, epi);
-        if (heavy)
-        {   // the queries the walk gave up on, eight lanes each; exits at once when there are none
-            const uint32_t GH = (uint32_t)std::max<size_t>(1, std::min(wave, (size_t)G));
-            search_heavy_kernel<K, Epi><<<dim3(GH, (unsigned)njobs), kChunk, 0, s>>>(d_clouds, d_jobs, D, gate, heavy,
-                                                                                    epi);
-            ws->launches++;
-        }
+                                                                              seed_nn, seed_k, epi);
     }
     else
     {
@@ -1490,48 +1484,73 @@ static int matcher_k(const IcpDevParams& D)
 }
 
 // the matcher's search: neighbour rows [job base + sorted position][K]
-static void launch_match_search(const ::b200icp* ctx, Workspace* ws, size_t max_points, size_t njobs,
-                                const CloudView* d_clouds, JobDev* d_jobs, uint32_t* d_nn, uint2* d_heavy)
+static void launch_match_search(const ::b200icp* ctx, Workspace* ws, const IcpDevParams& D, size_t max_points,
+                                size_t njobs, const CloudView* d_clouds, JobDev* d_jobs, uint32_t* d_nn)
 {
-    const IcpDevParams& D = ctx->D;
     const int           K = matcher_k(D);
     const bool          seeds = search_config().seeds;  // B200ICP_SEED=0: every search from the radius cap
     const NnWriter      w = {d_nn, nullptr, (uint32_t)K, 0u};
     if (K == 1)
-        launch_search_k<1>(ctx, ws, max_points, njobs, d_clouds, d_jobs, D, D.thr2, 1, w, d_heavy, seeds ? d_nn : nullptr,
+        launch_search_k<1>(ctx, ws, max_points, njobs, d_clouds, d_jobs, D, D.thr2, 1, w, seeds ? d_nn : nullptr,
                            (uint32_t)K);
     else if (K == 4)
-        launch_search_k<4>(ctx, ws, max_points, njobs, d_clouds, d_jobs, D, D.thr2, 1, w, d_heavy, seeds ? d_nn : nullptr,
+        launch_search_k<4>(ctx, ws, max_points, njobs, d_clouds, d_jobs, D, D.thr2, 1, w, seeds ? d_nn : nullptr,
                            (uint32_t)K);
     else if (K == 6)
-        launch_search_k<6>(ctx, ws, max_points, njobs, d_clouds, d_jobs, D, D.thr2, 1, w, d_heavy, seeds ? d_nn : nullptr,
+        launch_search_k<6>(ctx, ws, max_points, njobs, d_clouds, d_jobs, D, D.thr2, 1, w, seeds ? d_nn : nullptr,
                            (uint32_t)K);
     else
-        launch_search_k<8>(ctx, ws, max_points, njobs, d_clouds, d_jobs, D, D.thr2, 1, w, d_heavy, seeds ? d_nn : nullptr,
+        launch_search_k<8>(ctx, ws, max_points, njobs, d_clouds, d_jobs, D, D.thr2, 1, w, seeds ? d_nn : nullptr,
                            (uint32_t)K);
 }
 
+// tail_mode 1: the warp that completes a job's moment reduction runs the Gauss-Newton solver and the end of the
+// outer iteration; 0: the reduced moments are left in JobDev::M (Horn path, matcher hook)
 template <bool WRITE>
-static void launch_fit(Workspace* ws, const IcpDevParams& D, dim3 grid, const CloudView* d_clouds,
-                       const JobDev* d_jobs, const uint32_t* d_nn, double* d_partials, const MatchOut& mo,
-                       PairRec* d_pairs)
+static void launch_fit(Workspace* ws, const IcpDevParams& D, dim3 grid, const CloudView* d_clouds, JobDev* d_jobs,
+                       const uint32_t* d_nn, const FitBuffers& fb, uint32_t chunk_items, int tail_mode,
+                       const MatchOut& mo, PairRec* d_pairs, uint32_t* d_active)
 {
     cudaStream_t s = ws->stream;
     const int    K = matcher_k(D);
     if (K == 1)
-        fit_p2p_kernel<WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_nn, d_partials, D, mo, d_pairs);
+        fit_p2p_kernel<WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_nn, fb, chunk_items, tail_mode, D, mo, d_pairs,
+                                                      d_active);
     else if (K == 4)
-        fit_plane_kernel<4, WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_nn, d_partials, D, mo, d_pairs);
+        fit_plane_kernel<4, WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_nn, fb, chunk_items, tail_mode, D, mo,
+                                                           d_pairs, d_active);
     else if (K == 6)
-        fit_plane_kernel<6, WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_nn, d_partials, D, mo, d_pairs);
+        fit_plane_kernel<6, WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_nn, fb, chunk_items, tail_mode, D, mo,
+                                                           d_pairs, d_active);
     else
-        fit_plane_kernel<8, WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_nn, d_partials, D, mo, d_pairs);
+        fit_plane_kernel<8, WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_nn, fb, chunk_items, tail_mode, D, mo,
+                                                           d_pairs, d_active);
     ws->launches++;
 }
 
-static int check_supported(const ::b200icp* ctx)
+// Sizes baked into a replayed launch sequence (grids, offsets inside the scratch allocation) are taken from a
+// BUCKET of the point count -- four steps per octave -- so that scans whose size changes from frame to frame
+// (real LiDAR, decimated clouds) reuse one graph; the kernels read the true sizes from the device records.
+static size_t size_bucket(size_t n)
 {
-    const auto& P = ctx->P;
+    if (n <= 1024) return 1024;
+    size_t step = 1;
+    while ((step << 3) < n) step <<= 1;  // step = 2^(floor(log2(n - 1)) - 2)
+    return (n + step - 1) / step * step;
+}
+
+// items of the local cloud per chunk partial: 2 for a single registration (all warps of the machine get work:
+// 120k points -> 1875 chunks), more when many jobs share a launch (parallelism comes from the jobs and the
+// partials are 1.5 KB each)
+static uint32_t fit_chunk_items(size_t max_points, size_t njobs)
+{
+    if (njobs == 1) return 2;
+    const size_t items = (max_points + kItem - 1) / kItem;
+    return (uint32_t)std::min<size_t>(16, std::max<size_t>(2, items / 64));
+}
+
+static int check_supported(const IcpDevParams& P)
+{
     if ((P.matcher_kind != B200ICP_MATCHER_POINT2PLANE && P.matcher_kind != B200ICP_MATCHER_POINTS_DISTANCE) ||
         (P.solver_kind != B200ICP_SOLVER_GAUSS_NEWTON && P.solver_kind != B200ICP_SOLVER_HORN))
     {
@@ -1552,10 +1571,10 @@ static int check_supported(const ::b200icp* ctx)
 }
 
 // Jobs are processed in waves that bound gridDim.y.
-static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud* const* from,
-                    const b200icp_cloud* const* to, const double* guesses, b200icp_result_t* out)
+static int run_wave(::b200icp* ctx, Workspace* ws, const IcpDevParams& D, size_t n,
+                    const b200icp_cloud* const* from, const b200icp_cloud* const* to, const double* guesses,
+                    b200icp_result_t* out)
 {
-    const IcpDevParams& D = ctx->D;
     cudaStream_t        s = ws->stream;
     // unique cloud table
     std::map<const b200icp_cloud*, uint32_t> cmap;
@@ -1585,6 +1604,30 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
         max_points = std::max(max_points, to[j]->n);
         total_queries += to[j]->n;
     }
+    // chunk partials of the fit stage: where each job's partials / group partials / tickets start
+    const uint32_t chunk_items = fit_chunk_items(max_points, n);
+    uint64_t       total_chunks = 0, total_groups = 0;
+    for (size_t j = 0; j < n; j++)
+    {
+        const uint64_t items = (to[j]->n + kItem - 1) / kItem;
+        const uint64_t chunks = (items + chunk_items - 1) / chunk_items;
+        hjobs[j].chunk_base = (uint32_t)total_chunks;
+        hjobs[j].group_base = (uint32_t)total_groups;
+        total_chunks += chunks;
+        total_groups += (chunks + kFitGroup - 1) / kFitGroup;
+    }
+    if (total_chunks >= 0xFFFFFFFFull)
+    {
+        set_error("too many points in one batch");
+        return B200ICP_ERR_BAD_ARG;
+    }
+    // a single registration lays its buffers out for the size BUCKET of its clouds: offsets and grids then stay
+    // the same from scan to scan and the replayed graph with them
+    const size_t lay_points = (n == 1) ? size_bucket(max_points) : max_points;
+    const size_t lay_queries = (n == 1) ? size_bucket(total_queries) : (size_t)total_queries;
+    const size_t lay_chunks = (n == 1) ? ((lay_points + kItem - 1) / kItem + chunk_items - 1) / chunk_items
+                                       : (size_t)total_chunks;
+    const size_t lay_groups = (n == 1) ? (lay_chunks + kFitGroup - 1) / kFitGroup : (size_t)total_groups;
     const bool horn = (D.solver_kind == B200ICP_SOLVER_HORN);
     if (horn && total_queries >= 0xFFFFFFFFull)
     {
@@ -1593,37 +1636,38 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
     }
     for (auto& kv : cmap)
         if (int r = wait_cloud(ws, kv.first)) return r;
-    const uint32_t G = fit_ctas_per_job(ctx, max_points, n);
+    const uint32_t G = fit_ctas_per_job(ctx, lay_points, n, chunk_items);
     const int      K = matcher_k(D);
 
-    const uint32_t GH = std::max<uint32_t>(1, std::min<uint32_t>(G, (uint32_t)((max_points + 1023) / 1024)));
+    const uint32_t GH = std::max<uint32_t>(1, std::min<uint32_t>(G, (uint32_t)((lay_points + 1023) / 1024)));
     PairRec*       d_pairs = nullptr;
     double *       d_h0 = nullptr, *d_h1 = nullptr;
     uint32_t*      d_nn = nullptr;
-    uint2*         d_heavy = nullptr;
+    FitBuffers     fb = {nullptr, nullptr, nullptr};
     Carver sz(nullptr);
-    auto layout = [&](Carver& k, CloudView*& dc, JobDev*& dj, double*& dp, uint32_t*& da) {
+    auto layout = [&](Carver& k, CloudView*& dc, JobDev*& dj, uint32_t*& da) {
         dc = k.take<CloudView>(views.size());
         dj = k.take<JobDev>(n);
-        dp = k.take<double>((size_t)n * G * kNumMoments);
         da = k.take<uint32_t>(4);
-        d_nn = k.take<uint32_t>((total_queries ? total_queries : 1) * (size_t)K);
-        d_heavy = k.take<uint2>(total_queries ? total_queries : 1);
+        fb.tickets = k.take<uint32_t>(lay_groups ? lay_groups : 1);
+        fb.gpartials = k.take<double>((lay_groups ? lay_groups : 1) * (size_t)kNumMoments);
+        fb.partials = k.take<double>((lay_chunks ? lay_chunks : 1) * (size_t)kNumMoments);
+        d_nn = k.take<uint32_t>((lay_queries ? lay_queries : 1) * (size_t)K);
         if (horn)
         {
-            d_pairs = k.take<PairRec>(total_queries ? total_queries : 1);
+            d_pairs = k.take<PairRec>(lay_queries ? lay_queries : 1);
             d_h0 = k.take<double>((size_t)n * GH * kHornVals);
             d_h1 = k.take<double>((size_t)n * GH * kHornVals);
         }
     };
     CloudView* d_clouds;
     JobDev*    d_jobs;
-    double*    d_partials;
     uint32_t*  d_active;
-    layout(sz, d_clouds, d_jobs, d_partials, d_active);
+    layout(sz, d_clouds, d_jobs, d_active);
     if (int r = ws->reserve_device(sz.off)) return r;
     Carver real(ws->d_scratch);
-    layout(real, d_clouds, d_jobs, d_partials, d_active);
+    layout(real, d_clouds, d_jobs, d_active);
+    const size_t ticket_bytes = (lay_groups ? lay_groups : 1) * sizeof(uint32_t);
     // pinned staging: views | jobs | active flags (2 slots) | n_active init
     const size_t off_jobs = align_up(views.size() * sizeof(CloudView));
     const size_t off_flags = off_jobs + align_up(n * sizeof(JobDev));
@@ -1641,6 +1685,7 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
         cudaError_t e = cudaMemcpyAsync(d_clouds, h_views, views.size() * sizeof(CloudView), cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_jobs, h_jobs, n * sizeof(JobDev), cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_active, h_flags + 2, sizeof(uint32_t), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(fb.tickets, 0, ticket_bytes, s);  // arrival counters of the fit stage
         if (e != cudaSuccess) setup_err = e;
     };
 
@@ -1658,7 +1703,7 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
     // the same number of iterations -- and checks it right away.
     cudaError_t eval_err = cudaSuccess;
     auto evaluate = [&]() {
-        launch_search_k<1>(ctx, ws, max_points, n, d_clouds, d_jobs, D, D.q_thr2, 2, HitCounter{D.q_thr2}, d_heavy,
+        launch_search_k<1>(ctx, ws, lay_points, n, d_clouds, d_jobs, D, D.q_thr2, 2, HitCounter{D.q_thr2},
                            search_config().seeds ? d_nn : nullptr, (uint32_t)K);
         covariance_kernel<<<(unsigned)n, 64, 0, s>>>(d_jobs, D);
         ws->launches++;
@@ -1678,8 +1723,10 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
     bool graphed = false;
     if (predict && !prof && !horn && search_config().graphs && first <= D.max_iterations)
     {
-        const AlignGraphKey key = {ws->d_scratch, ws->h_pinned, (uint64_t)max_points, (uint64_t)total_queries,
-                                   (uint32_t)views.size(), G, first, (uint32_t)matcher_k(D)};
+        uint64_t phash = 1469598103934665603ull;  // the parameter block is baked into the kernel nodes
+        for (size_t b = 0; b < sizeof(D); b++) phash = (phash ^ reinterpret_cast<const unsigned char*>(&D)[b]) * 1099511628211ull;
+        const AlignGraphKey key = {ws->d_scratch, ws->h_pinned, (uint64_t)lay_points, (uint64_t)lay_queries,
+                                   (uint32_t)views.size(), G, first, (uint32_t)matcher_k(D), phash};
         cudaGraphExec_t exec = ws->find_align_graph(key);
         if (!exec && !ws->graph_failed)
         {
@@ -1691,10 +1738,8 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
                 enqueue_setup();
                 for (uint32_t i = 0; i < first; i++)
                 {
-                    launch_match_search(ctx, ws, max_points, n, d_clouds, d_jobs, d_nn, d_heavy);
-                    launch_fit<false>(ws, D, mgrid, d_clouds, d_jobs, d_nn, d_partials, no_out, d_pairs);
-                    solve_kernel<<<(unsigned)n, kSolveThreads, 0, s>>>(d_clouds, d_jobs, d_partials, G, D, d_active);
-                    ws->launches++;
+                    launch_match_search(ctx, ws, D, lay_points, n, d_clouds, d_jobs, d_nn);
+                    launch_fit<false>(ws, D, mgrid, d_clouds, d_jobs, d_nn, fb, chunk_items, 1, no_out, d_pairs, d_active);
                 }
                 evaluate();
                 cudaMemcpyAsync(h_flags, d_active, sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
@@ -1740,23 +1785,20 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
         for (uint32_t i = 0; i < todo; i++, enq++)
         {
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 0], s));
-            launch_match_search(ctx, ws, max_points, n, d_clouds, d_jobs, d_nn, d_heavy);
+            launch_match_search(ctx, ws, D, lay_points, n, d_clouds, d_jobs, d_nn);
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 1], s));
-            launch_fit<false>(ws, D, mgrid, d_clouds, d_jobs, d_nn, d_partials, no_out, d_pairs);
+            // Gauss-Newton: the fit kernel's last warp per job solves and ends the iteration; Horn: the fit leaves
+            // the matcher's moments in the job record and the closed-form solver follows
+            launch_fit<false>(ws, D, mgrid, d_clouds, d_jobs, d_nn, fb, chunk_items, horn ? 0 : 1, no_out, d_pairs,
+                              d_active);
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 2], s));
             if (horn)
             {
                 const dim3 hgrid(GH, (unsigned)n);
                 horn_sum_kernel<<<hgrid, kHornThreads, 0, s>>>(d_clouds, d_jobs, d_pairs, nullptr, d_h0, D, 0);
                 horn_sum_kernel<<<hgrid, kHornThreads, 0, s>>>(d_clouds, d_jobs, d_pairs, d_h0, d_h1, D, 1);
-                horn_solve_kernel<<<(unsigned)n, kSolveThreads, 0, s>>>(d_jobs, d_partials, G, d_h0, d_h1, GH, D,
-                                                                        d_active);
+                horn_solve_kernel<<<(unsigned)n, kHornSolveThreads, 0, s>>>(d_jobs, d_h0, d_h1, GH, D, d_active);
                 ws->launches += 3;
-            }
-            else
-            {
-                solve_kernel<<<(unsigned)n, kSolveThreads, 0, s>>>(d_clouds, d_jobs, d_partials, G, D, d_active);
-                ws->launches++;
             }
             if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[4 * enq + 3], s));
         }
@@ -1809,6 +1851,11 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
         max_runs = std::max(max_runs, runs);
     }
     if (n == 1) ctx->expected_runs.store((int)max_runs);
+    if (getenv("B200ICP_DBG_TAIL"))
+        fprintf(stderr, "[dbg tail] job 0: final moment sum %u cycles, GN loop %u cycles (%u inner), end of iteration %u "
+                        "cycles; %u outer iterations, %u inner in total\n",
+                h_jobs[0].dbg_tail[0], h_jobs[0].dbg_tail[1], h_jobs[0].dbg_tail[3], h_jobs[0].dbg_tail[2],
+                h_jobs[0].iter, h_jobs[0].inner_iters_total);
     if (prof)
     {
         double mm = 0, fm = 0, sm = 0;
@@ -1833,10 +1880,31 @@ static int run_wave(::b200icp* ctx, Workspace* ws, size_t n, const b200icp_cloud
     return B200ICP_OK;
 }
 
-int run_align_batch(::b200icp* ctx, size_t n, const b200icp_cloud* const* from,
-                    const b200icp_cloud* const* to, const double* guesses, b200icp_result_t* out)
+// mp2p_icp::Parameters of ONE call over the object's own (LidarOdometry.cpp:869-871 hands in.icp_params to
+// align() next to the shared ICP object, whose matchers / solvers / quality evaluators stay as configured)
+static IcpDevParams merged_params(const ::b200icp* ctx, const b200icp_call_params_t* call)
 {
-    if (int r = check_supported(ctx)) return r;
+    IcpDevParams D = ctx->D;
+    if (call)
+    {
+        D.max_iterations = call->max_iterations;
+        D.min_abs_step_trans = call->min_abs_step_trans;
+        D.min_abs_step_rot = call->min_abs_step_rot;
+        D.use_scale_outlier_detector = call->use_scale_outlier_detector;
+        D.scale_outlier_threshold = call->scale_outlier_threshold;
+        D.use_robust_kernel = call->use_robust_kernel;
+        D.robust_kernel_param = call->robust_kernel_param;
+        D.robust_kernel_scale = call->robust_kernel_scale;
+    }
+    return D;
+}
+
+int run_align_batch(::b200icp* ctx, size_t n, const b200icp_cloud* const* from,
+                    const b200icp_cloud* const* to, const double* guesses, const b200icp_call_params_t* call,
+                    b200icp_result_t* out)
+{
+    const IcpDevParams D = merged_params(ctx, call);
+    if (int r = check_supported(D)) return r;
     if (n == 0) return B200ICP_OK;
     Lease L(ctx);
     if (!L.ws) return B200ICP_ERR_CUDA;
@@ -1847,7 +1915,7 @@ int run_align_batch(::b200icp* ctx, size_t n, const b200icp_cloud* const* from,
         size_t cnt = 0, queries = 0;
         while (i + cnt < n && cnt < kWaveJobs && (cnt == 0 || queries + to[i + cnt]->n <= kWaveQueries))
             queries += to[i + cnt]->n, cnt++;
-        if (int r = run_wave(ctx, L.ws, cnt, from + i, to + i, guesses + 6 * i, out + i)) return r;
+        if (int r = run_wave(ctx, L.ws, D, cnt, from + i, to + i, guesses + 6 * i, out + i)) return r;
         i += cnt;
     }
     return B200ICP_OK;
@@ -1859,7 +1927,6 @@ struct SingleJob
 {
     CloudView* d_clouds = nullptr;
     JobDev*    d_jobs = nullptr;
-    uint2*     d_heavy = nullptr;  // heavy-query list of the search (one entry per query at most)
     Pose       T;
 };
 
@@ -1873,7 +1940,6 @@ static int single_job_setup(Workspace* ws, const b200icp_cloud* from, const b200
     auto layout = [&](Carver& c) {
         sj.d_clouds = c.take<CloudView>(2);
         sj.d_jobs = c.take<JobDev>(1);
-        sj.d_heavy = c.take<uint2>(to->n ? to->n : 1);
         extra(c);
     };
     Carver sz(nullptr);
@@ -1953,13 +2019,13 @@ int run_knn(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, co
 #endif
     }
     if (k == 1)
-        launch_search_k<1>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
+        launch_search_k<1>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
     else if (k <= 4)
-        launch_search_k<4>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
+        launch_search_k<4>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
     else if (k <= 6)
-        launch_search_k<6>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
+        launch_search_k<6>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
     else
-        launch_search_k<8>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
+        launch_search_k<8>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
     if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[1], s));
     B2_CUDA_TRY(cudaGetLastError());
     if (d_dbg)
@@ -2098,13 +2164,13 @@ int run_knn_keys(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* 
     }
     const KeyWriter w = {d_keys_out, d_index_map, k};
     if (k == 1)
-        launch_search_k<1>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
+        launch_search_k<1>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
     else if (k <= 4)
-        launch_search_k<4>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
+        launch_search_k<4>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
     else if (k <= 6)
-        launch_search_k<6>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
+        launch_search_k<6>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
     else
-        launch_search_k<8>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
+        launch_search_k<8>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
     if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[1], s));
     B2_CUDA_TRY(cudaGetLastError());
     B2_CUDA_TRY(cudaStreamSynchronize(s));
@@ -2158,13 +2224,13 @@ static int enqueue_scatter(::b200icp* ctx, Workspace* ws, const b200icp_cloud* r
         B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[0], s));
     }
     if (k == 1)
-        launch_search_k<1>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
+        launch_search_k<1>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
     else if (k <= 4)
-        launch_search_k<4>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
+        launch_search_k<4>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
     else if (k <= 6)
-        launch_search_k<6>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
+        launch_search_k<6>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
     else
-        launch_search_k<8>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w, sj.d_heavy);
+        launch_search_k<8>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
     if (time_it) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[1], s));
     B2_CUDA_TRY(cudaGetLastError());
     return B200ICP_OK;
@@ -2383,7 +2449,7 @@ int run_match(::b200icp* ctx, const b200icp_cloud* from, const b200icp_cloud* to
               const double* pose6, uint8_t* paired, uint32_t* nn_idx, uint32_t* nn_cnt,
               double* centroid, double* normal, uint32_t* n_pairings)
 {
-    if (int r = check_supported(ctx)) return r;
+    if (int r = check_supported(ctx->D)) return r;
     Lease L(ctx);
     if (!L.ws) return B200ICP_ERR_CUDA;
     Workspace*          ws = L.ws;
@@ -2392,14 +2458,19 @@ int run_match(::b200icp* ctx, const b200icp_cloud* from, const b200icp_cloud* to
     const size_t        n = to->n, k = (D.matcher_kind == B200ICP_MATCHER_POINTS_DISTANCE) ? 1 : D.knn;
     if (n_pairings) *n_pairings = 0;
     if (n == 0) return B200ICP_OK;
-    const uint32_t G = fit_ctas_per_job(ctx, n, 1);
-    double*        d_partials = nullptr;
+    const uint32_t chunk_items = fit_chunk_items(n, 1);
+    const uint32_t G = fit_ctas_per_job(ctx, n, 1, chunk_items);
+    const size_t   chunks = ((n + kItem - 1) / kItem + chunk_items - 1) / chunk_items;
+    const size_t   groups = (chunks + kFitGroup - 1) / kFitGroup;
+    FitBuffers     fb = {nullptr, nullptr, nullptr};
     uint32_t*      d_nn = nullptr;
     MatchOut       mo;
     SingleJob      sj;
     // the matcher is active at iteration run_from_iteration
     if (int r = single_job_setup(ws, from, to, pose6, D.run_from_iteration, sj, [&](Carver& c) {
-            d_partials = c.take<double>((size_t)G * kNumMoments);
+            fb.tickets = c.take<uint32_t>(groups ? groups : 1);
+            fb.gpartials = c.take<double>((groups ? groups : 1) * (size_t)kNumMoments);
+            fb.partials = c.take<double>((chunks ? chunks : 1) * (size_t)kNumMoments);
             d_nn = c.take<uint32_t>(n * (size_t)matcher_k(D));
             mo.paired = c.take<uint8_t>(n);
             mo.nn_idx = c.take<uint32_t>(n * k);
@@ -2408,17 +2479,17 @@ int run_match(::b200icp* ctx, const b200icp_cloud* from, const b200icp_cloud* to
             mo.normal = c.take<double>(n * 3);
         }))
         return r;
+    B2_CUDA_TRY(cudaMemsetAsync(fb.tickets, 0, (groups ? groups : 1) * sizeof(uint32_t), s));
     B2_CUDA_TRY(cudaMemsetAsync(mo.paired, 0, n, s));
     B2_CUDA_TRY(cudaMemsetAsync(mo.nn_cnt, 0, n * sizeof(uint32_t), s));
     B2_CUDA_TRY(cudaMemsetAsync(mo.nn_idx, 0xFF, n * k * sizeof(uint32_t), s));
     B2_CUDA_TRY(cudaMemsetAsync(mo.centroid, 0, n * 3 * sizeof(double), s));
     B2_CUDA_TRY(cudaMemsetAsync(mo.normal, 0, n * 3 * sizeof(double), s));
-    launch_match_search(ctx, ws, n, 1, sj.d_clouds, sj.d_jobs, d_nn, sj.d_heavy);
-    launch_fit<true>(ws, D, dim3(G, 1), sj.d_clouds, sj.d_jobs, d_nn, d_partials, mo, nullptr);
+    launch_match_search(ctx, ws, D, n, 1, sj.d_clouds, sj.d_jobs, d_nn);
+    launch_fit<true>(ws, D, dim3(G, 1), sj.d_clouds, sj.d_jobs, d_nn, fb, chunk_items, 0, mo, nullptr, nullptr);
     B2_CUDA_TRY(cudaGetLastError());
-    std::vector<double> part((size_t)G * kNumMoments);
-    B2_CUDA_TRY(cudaMemcpyAsync(part.data(), d_partials, part.size() * sizeof(double),
-                                cudaMemcpyDeviceToHost, s));
+    JobDev* hj = (JobDev*)((char*)ws->h_pinned + align_up(2 * sizeof(CloudView)));  // the reduced moments come back
+    B2_CUDA_TRY(cudaMemcpyAsync(hj, sj.d_jobs, sizeof(JobDev), cudaMemcpyDeviceToHost, s));
     if (paired) B2_CUDA_TRY(cudaMemcpyAsync(paired, mo.paired, n, cudaMemcpyDeviceToHost, s));
     if (nn_idx)
         B2_CUDA_TRY(cudaMemcpyAsync(nn_idx, mo.nn_idx, n * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -2430,12 +2501,7 @@ int run_match(::b200icp* ctx, const b200icp_cloud* from, const b200icp_cloud* to
         B2_CUDA_TRY(cudaMemcpyAsync(normal, mo.normal, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
     B2_CUDA_TRY(cudaStreamSynchronize(s));
     if (n_pairings)
-    {
-        double cnt = 0;
-        const bool p2p = (D.matcher_kind == B200ICP_MATCHER_POINTS_DISTANCE);
-        for (uint32_t c = 0; c < G; c++) cnt += pairing_count(part.data() + (size_t)c * kNumMoments, p2p);
-        *n_pairings = (uint32_t)(cnt + 0.5);
-    }
+        *n_pairings = (uint32_t)(pairing_count(hj->M, D.matcher_kind == B200ICP_MATCHER_POINTS_DISTANCE) + 0.5);
     return B200ICP_OK;
 }
 

@@ -421,7 +421,35 @@ extern "C" int b200icp_align(b200icp_t* icp, const b200icp_cloud_t* from_global,
     }
     const b200icp_cloud_t* f[1] = {from_global};
     const b200icp_cloud_t* t[1] = {to_local};
-    return run_align_batch(icp, 1, f, t, guess6, out);
+    return run_align_batch(icp, 1, f, t, guess6, nullptr, out);
+}
+
+extern "C" void b200icp_call_params_of(const b200icp_params_t* p, b200icp_call_params_t* out)
+{
+    if (!p || !out) return;
+    memset(out, 0, sizeof(*out));
+    out->max_iterations = p->max_iterations;
+    out->min_abs_step_trans = p->min_abs_step_trans;
+    out->min_abs_step_rot = p->min_abs_step_rot;
+    out->use_scale_outlier_detector = p->use_scale_outlier_detector;
+    out->scale_outlier_threshold = p->scale_outlier_threshold;
+    out->use_robust_kernel = p->use_robust_kernel;
+    out->robust_kernel_param = p->robust_kernel_param;
+    out->robust_kernel_scale = p->robust_kernel_scale;
+}
+
+extern "C" int b200icp_align_with(b200icp_t* icp, const b200icp_cloud_t* from_global,
+                                  const b200icp_cloud_t* to_local, const double guess6[6],
+                                  const b200icp_call_params_t* call, b200icp_result_t* out)
+{
+    if (!icp || !from_global || !to_local || !guess6 || !out)
+    {
+        set_error("null argument");
+        return B200ICP_ERR_BAD_ARG;
+    }
+    const b200icp_cloud_t* f[1] = {from_global};
+    const b200icp_cloud_t* t[1] = {to_local};
+    return run_align_batch(icp, 1, f, t, guess6, call, out);
 }
 
 extern "C" int b200icp_align_batch(b200icp_t* icp, size_t n, const b200icp_cloud_t* const* from_global,
@@ -439,7 +467,7 @@ extern "C" int b200icp_align_batch(b200icp_t* icp, size_t n, const b200icp_cloud
             set_error("null cloud in job %zu", i);
             return B200ICP_ERR_BAD_ARG;
         }
-    return run_align_batch(icp, n, from_global, to_local, guesses6, out);
+    return run_align_batch(icp, n, from_global, to_local, guesses6, nullptr, out);
 }
 
 extern "C" void b200icp_profile_enable(b200icp_t* icp, int enable)

@@ -157,7 +157,7 @@ __device__ __forceinline__ void scan_plain(const float4* __restrict__ pts, uint3
 }
 
 #ifndef B200ICP_PLAIN_RUN
-#define B200ICP_PLAIN_RUN 6
+#define B200ICP_PLAIN_RUN 16
 #endif
 constexpr uint32_t kPlainRun = B200ICP_PLAIN_RUN;  // runs up to this length are scanned without looking at group boxes
 
@@ -215,17 +215,16 @@ __device__ __forceinline__ void scan_range(const float4* __restrict__ pts, const
 
 // keys must be initialised by the caller with sentinel_key(cap_d2).
 template <int K>
-__device__ __forceinline__ bool knn_search(const CloudView& cv, const GridDev& g, float qx,
-                                           float qy, float qz, float cap_d2, uint32_t budget,
+__device__ __forceinline__ void knn_search(const CloudView& cv, const GridDev& g, float qx,
+                                           float qy, float qz, float cap_d2,
                                            uint64_t (&key)[K])
 {
-    uint32_t used = 0;
     const float inv = g.inv_cell;
     // shells of fine cells that can hold a point within the cap
     const int   S = max(1, (int)ceilf(sqrtf(cap_d2) * inv * 1.0005f));
     const float lim_lo = -(float)(S + 2), lim_hi = (float)(kFineMax + S + 3);
     float       ux = (qx - g.ox) * inv, uy = (qy - g.oy) * inv, uz = (qz - g.oz) * inv;
-    if (!(ux == ux) || !(uy == uy) || !(uz == uz)) return true;  // NaN query: no neighbours
+    if (!(ux == ux) || !(uy == uy) || !(uz == uz)) return;  // NaN query: no neighbours
     ux = fminf(fmaxf(ux, lim_lo), lim_hi);
     uy = fminf(fmaxf(uy, lim_lo), lim_hi);
     uz = fminf(fmaxf(uz, lim_lo), lim_hi);
@@ -288,14 +287,11 @@ __device__ __forceinline__ bool knn_search(const CloudView& cv, const GridDev& g
                         const uint32_t end = __ldg(cv.fine_start + ord + 1);
                         scan_range<K>(cv.pts, cv.gbox, beg, end, qx, qy, qz, key);
                         worst = key_d2(key[K - 1]) * to_cells2;
-                        used += end - beg;
-                        if (used > budget) return false;
                     }
                 }
             }
         }
     }
-    return true;
 }
 
 }  // namespace b2

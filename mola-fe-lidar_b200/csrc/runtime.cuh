@@ -56,11 +56,12 @@ struct AlignGraphKey
     void*    h_pinned;
     uint64_t max_points, total_queries;
     uint32_t n_views, fit_ctas, first, k;
+    uint64_t params_hash;
     bool operator==(const AlignGraphKey& o) const
     {
         return d_scratch == o.d_scratch && h_pinned == o.h_pinned && max_points == o.max_points &&
                total_queries == o.total_queries && n_views == o.n_views && fit_ctas == o.fit_ctas &&
-               first == o.first && k == o.k;
+               first == o.first && k == o.k && params_hash == o.params_hash;
     }
 };
 
@@ -199,7 +200,8 @@ int cloud_alloc(::b200icp* ctx, Workspace* ws, size_t n, float search_radius, b2
 int cloud_build_index(::b200icp* ctx, Workspace* ws, b200icp_cloud* c);
 
 int run_align_batch(::b200icp* ctx, size_t n, const b200icp_cloud* const* from,
-                    const b200icp_cloud* const* to, const double* guesses, b200icp_result_t* out);
+                    const b200icp_cloud* const* to, const double* guesses, const b200icp_call_params_t* call,
+                    b200icp_result_t* out);
 int run_knn(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, const double* pose6,
             uint32_t k, float max_dist, uint32_t* idx_out, float* d2_out);
 int run_knn_keys(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, const double* pose6,

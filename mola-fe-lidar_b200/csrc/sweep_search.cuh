@@ -124,7 +124,7 @@ __device__ __forceinline__ void sweep_search(float4* buf, const CloudView& cv, c
     const int   nb = nbx * nby * nbz;
     if (nbx > 64 || nby > 64 || nbz > 64 || nb > kSweepMaxBlocks)
     {  // very spread item: per-lane walk over the hash, same results
-        if (part == 0 && valid) knn_search<K>(cv, g, qx, qy, qz, cap_d2, 0xFFFFFFFFu, key);
+        if (part == 0 && valid) knn_search<K>(cv, g, qx, qy, qz, cap_d2, key);
         return;
     }
     // lanes without a query evaluate against a point at infinity: never inserted

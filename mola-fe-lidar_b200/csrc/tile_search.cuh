@@ -185,16 +185,11 @@ __device__ __forceinline__ uint2 tile_cell_range(const WarpTile& W, const TileGe
 }
 
 // Per-lane search inside a built tile. keys must hold sentinel_key(cap_d2).
-// Returns false when the lane gave up after scanning more than `budget`
-// candidates (its list is then a valid partial result: real points, and
-// key[K-1] bounds the k-th nearest from above once the list is full); such
-// queries are finished by the cooperative search (coop_search.cuh).
 template <int K>
-__device__ __forceinline__ bool tile_knn(const WarpTile& W, const TileGeom& G, const CloudView& cv,
+__device__ __forceinline__ void tile_knn(const WarpTile& W, const TileGeom& G, const CloudView& cv,
                                          const GridDev& g, const QueryCell& q, int S, float qx,
-                                         float qy, float qz, uint32_t budget, uint64_t (&key)[K])
+                                         float qy, float qz, uint64_t (&key)[K])
 {
-    uint32_t used = 0;
     const int   ny = G.ny;
     const int   hx = q.hx - G.t0x, hy = q.hy - G.t0y, hz = q.hz - G.t0z;
     const float slack = g.slack;
@@ -240,13 +235,10 @@ __device__ __forceinline__ bool tile_knn(const WarpTile& W, const TileGeom& G, c
                     const uint2 c = tile_cell_range(W, G, cv, x, y, hz + dz);
                     scan_range<K>(cv.pts, cv.gbox, c.x, c.y, qx, qy, qz, key);
                     worst = key_d2(key[K - 1]) * to_cells2;
-                    used += c.y - c.x;
-                    if (used > budget) return false;
                 }
             }
         }
     }
-    return true;
 }
 
 // global warp id / warp count of a (G, jobs) launch of kChunk-thread CTAs

@@ -209,13 +209,19 @@ int run_voxel(::b200icp* ctx, const b200icp_cloud* in, float resolution, int use
     if (int r = cloud_alloc(ctx, ws, m, search_radius, &c)) return r;
     if (m)
     {
-        B2_CUDA_TRY(cudaMemcpyAsync(c->dx, ox, m * sizeof(float), cudaMemcpyDeviceToDevice, s));
-        B2_CUDA_TRY(cudaMemcpyAsync(c->dy, oy, m * sizeof(float), cudaMemcpyDeviceToDevice, s));
-        B2_CUDA_TRY(cudaMemcpyAsync(c->dz, oz, m * sizeof(float), cudaMemcpyDeviceToDevice, s));
-        if (keep_idx)
+        cudaError_t e = cudaMemcpyAsync(c->dx, ox, m * sizeof(float), cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->dy, oy, m * sizeof(float), cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->dz, oz, m * sizeof(float), cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess && keep_idx)
         {
-            B2_CUDA_TRY(cudaMemcpyAsync(keep_idx, keep, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-            B2_CUDA_TRY(cudaStreamSynchronize(s));
+            e = cudaMemcpyAsync(keep_idx, keep, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        }
+        if (e != cudaSuccess)
+        {   // the new cloud must not outlive a failed copy
+            set_error("voxel output copy failed: %s", cudaGetErrorString(e));
+            b200icp_cloud_free(c);
+            return B200ICP_ERR_CUDA;
         }
     }
     // the scratch holding ox/oy/oz is reused by the index build: the D2D copies

@@ -78,13 +78,24 @@ LidarOdometry::~LidarOdometry()
 {
     worker_pool_.clear();
     worker_pool_past_KFs_.clear();
-    state_ = MethodState();
-    if (worldmodel_) worldmodel_->clear();
     release_icp_objects();
 }
 
+// Every device cloud this module made holds its ICP object's context (uploads, spills and reloads go through
+// it): they go first -- the last scan, the key-frame clouds annotated in the world model (only THIS module's
+// annotation; a world model injected with setWorldModel() may be shared with other modules) -- and only then
+// the ICP objects.  Callers make sure no pool task is running (destructor: pools cleared; initialize: waitIdle).
 void LidarOdometry::release_icp_objects()
 {
+    {
+        std::lock_guard<std::mutex> lk(state_mtx_);
+        state_ = MethodState();
+    }
+    if (worldmodel_) worldmodel_->erase_annotation_everywhere(ANNOTATION_NAME_PC_LAYERS);
+    {
+        std::lock_guard<std::mutex> lk(kf_store_mtx_);
+        kf_store_.clear();
+    }
     for (auto& kv : params_.icp)
     {
         b200icp_destroy(kv.second.icp);
@@ -137,6 +148,7 @@ void LidarOdometry::initialize(const Yaml& c)
         params_.montecarlo_seed = seed;
     }
 
+    waitIdle();  // a second initialize(): nothing may still be using the objects released next
     release_icp_objects();
     cfg.at("icp_settings_with_vel");  // ENSURE_YAML_ENTRY_EXISTS cpp:122
     load_icp_set_of_params(params_.icp[AlignKind::LidarOdometry], cfg["icp_settings_with_vel"], params_.device);
@@ -184,7 +196,11 @@ void LidarOdometry::initialize(const Yaml& c)
 
 void LidarOdometry::spinOnce() { ProfilerEntry tleg(profiler_, "spinOnce"); }  // cpp:150-158
 
-void LidarOdometry::reset() { state_ = MethodState(); }  // cpp:160
+void LidarOdometry::reset()  // cpp:160
+{
+    std::lock_guard<std::mutex> lk(state_mtx_);
+    state_ = MethodState();
+}
 
 void LidarOdometry::waitIdle()
 {
@@ -204,6 +220,7 @@ void LidarOdometry::onNewObservation(CObservation::Ptr& o)
     if (queued > 10)
     {
         profiler_.registerUserMeasure("onNewObservation.drop_observation", 1);
+        std::lock_guard<std::mutex> lk(state_mtx_);
         state_.n_dropped++;
         return;
     }
@@ -288,9 +305,10 @@ void LidarOdometry::doProcessNewObservation(CObservation::Ptr& o)
             icp_in.to_id = INVALID_ID;  // current data, not a new KF (yet)
             icp_in.debug_str = "lidar_odom";
             // If we don't have a valid twist estimation, use the other set (cpp:287-290)
-            icp_in.icp_params = state_.last_iter_twist_is_good
-                                    ? params_.icp[AlignKind::LidarOdometry].icpParameters
-                                    : params_.icp[AlignKind::NearbyAlign].icpParameters;
+            b200icp_call_params_of(state_.last_iter_twist_is_good
+                                       ? &params_.icp[AlignKind::LidarOdometry].icpParameters
+                                       : &params_.icp[AlignKind::NearbyAlign].icpParameters,
+                                   &icp_in.icp_params);
             profiler_.leave("doProcessNewObservation.2c.prepare_icp_in");
             {
                 ProfilerEntry tle(profiler_, "doProcessNewObservation.3.icp_latest");
@@ -476,14 +494,14 @@ void LidarOdometry::checkForNearbyKFs()
             {
                 d->align_kind = AlignKind::NearbyAlign;
                 d->debug_str = "extra_edge";
-                d->icp_params = params_.icp[d->align_kind].icpParameters;
+                b200icp_call_params_of(&params_.icp[d->align_kind].icpParameters, &d->icp_params);
                 nearby_checks.emplace_back(std::move(d));
             }
             else
             {
                 d->align_kind = AlignKind::LoopClosure;
                 d->debug_str = "loop_closure";
-                d->icp_params = params_.icp[d->align_kind].icpParameters;
+                b200icp_call_params_of(&params_.icp[d->align_kind].icpParameters, &d->icp_params);
                 loop_closure_checks[kf_eucl_dist] = std::move(d);
             }
         }
@@ -553,7 +571,7 @@ void LidarOdometry::doCheckForNonAdjacentKFs(ICP_Input::Ptr d)
             check_rc(b200icp_align_batch(params_.icp.at(d->align_kind).icp, N, fr.data(), to.data(),
                                          guesses.data(), res.data()),
                      "b200icp_align_batch");
-            state_.n_icp += N;
+            count_icp(N);
             kf_store_enforce_budget();
             for (size_t i = 0; i < N; i++)
             {
@@ -652,26 +670,18 @@ void LidarOdometry::run_one_icp(const ICP_Input& in, ICP_Output& out)
     b200icp_result_t icp_result;
     const double     guess[6] = {current_solution.x,   current_solution.y,     current_solution.z,
                              current_solution.yaw, current_solution.pitch, current_solution.roll};
-    // the ICP object of `align_kind` runs with the Parameters the caller
-    // selected (cpp:869-871 passes in.icp_params next to the shared object)
-    auto&      the_case = params_.icp.at(in.align_kind);
-    b200icp_t* icp = the_case.icp;
-    b200icp_t* tmp = nullptr;
-    if (memcmp(&in.icp_params, &the_case.icpParameters, sizeof(b200icp_params_t)) != 0)
-    {
-        check_rc(b200icp_create(&in.icp_params, params_.device, &tmp), "b200icp_create");
-        icp = tmp;
-    }
-    int rc;
+    // the ICP object of `align_kind` -- its matchers, solvers and quality evaluators -- runs with the
+    // mp2p_icp::Parameters the caller selected (cpp:869-871 passes in.icp_params next to the shared object)
+    b200icp_t* icp = params_.icp.at(in.align_kind).icp;
+    int        rc;
     {
         CloudPin pin_from(in.from_pc), pin_to(in.to_pc);  // resident (re-uploaded if spilled) for the call
         if (!pin_from.h || !pin_to.h) throw std::runtime_error(std::string("cloud reload: ") + b200icp_last_error());
-        rc = b200icp_align(icp, pin_from.h, pin_to.h, guess, &icp_result);
+        rc = b200icp_align_with(icp, pin_from.h, pin_to.h, guess, &in.icp_params, &icp_result);
     }
-    if (tmp) b200icp_destroy(tmp);
     check_rc(rc, "b200icp_align");
     kf_store_enforce_budget();  // a reload may have pushed the store over its budget
-    state_.n_icp++;
+    count_icp(1);
 
     if (icp_result.quality > 0)
     {  // Keep as init value for next stage (cpp:873-877)

@@ -144,8 +144,10 @@ class LidarOdometry : public FrontEndBase
         id_t             from_id{INVALID_ID};
         DeviceCloud::Ptr to_pc, from_pc;
         TPose3D          init_guess_to_wrt_from;
-        b200icp_params_t icp_params;
-        std::string      debug_str;
+        /** mp2p_icp::Parameters of this call (h:121): the iteration budget, tolerances and pairing weights.
+         *  The matchers / solvers / quality evaluators are those of the `align_kind` object (cpp:869-871). */
+        b200icp_call_params_t icp_params;
+        std::string           debug_str;
     };
     struct ICP_Output
     {
@@ -177,8 +179,14 @@ class LidarOdometry : public FrontEndBase
         size_t     n_processed{0}, n_dropped{0}, n_icp{0};
     };
 
+    /** Like the reference (h:163) the state belongs to the 1-thread pool; the counters the other pool's
+     *  threads bump (n_icp) and the copy for harnesses are taken under state_mtx_. */
     const MethodState& state() const { return state_; }
-    MethodState        stateCopy() const { return state_; }
+    MethodState        stateCopy() const
+    {
+        std::lock_guard<std::mutex> lk(state_mtx_);
+        return state_;
+    }
 
     /** blocks until both worker pools are idle (harness helper) */
     void waitIdle();
@@ -209,8 +217,14 @@ class LidarOdometry : public FrontEndBase
     std::mutex                                 kf_store_mtx_;
     std::vector<std::weak_ptr<DeviceCloud>>    kf_store_;
 
-    std::mutex local_pose_graph_mtx;
-    float      cloud_search_radius_{0.f};
+    std::mutex         local_pose_graph_mtx;
+    mutable std::mutex state_mtx_;  // n_icp / n_dropped (touched by several threads) and stateCopy()
+    float              cloud_search_radius_{0.f};
+    void               count_icp(size_t n)
+    {
+        std::lock_guard<std::mutex> lk(state_mtx_);
+        state_.n_icp += n;
+    }
 };
 
 }  // namespace mola

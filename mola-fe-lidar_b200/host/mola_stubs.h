@@ -237,6 +237,13 @@ class WorldModel
         annotations_.clear();
         adjacency_.clear();
     }
+    /** drops one named annotation from every entity (a module removing what IT put there) */
+    void erase_annotation_everywhere(const std::string& name)
+    {
+        ent_mtx_.lock();
+        for (auto& kv : annotations_) kv.second.erase(name);
+        ent_mtx_.unlock();
+    }
 
    private:
     std::shared_mutex                                          ent_mtx_, fac_mtx_;

@@ -95,18 +95,30 @@ class TimeLogger
         size_t n = 0;
         double total = 0, min = 1e300, max = 0;
     };
+    // Open sections are kept per (name, thread): run_one_icp / doCheckForNonAdjacentKFs run concurrently on the
+    // pool threads.  A section left on another thread than it was entered on (delay_onNewObs_to_process:
+    // entered by the data source's thread, left by the worker) closes the oldest open one of that name.
     void enter(const std::string& name)
     {
         std::lock_guard<std::mutex> lk(mtx_);
-        open_[name] = now();
+        open_.emplace(name, Open{std::this_thread::get_id(), now()});
     }
     double leave(const std::string& name)
     {
         std::lock_guard<std::mutex> lk(mtx_);
-        auto                        it = open_.find(name);
-        if (it == open_.end()) return 0;
-        const double dt = now() - it->second;
-        open_.erase(it);
+        auto                        range = open_.equal_range(name);
+        if (range.first == range.second) return 0;
+        auto pick = range.second;
+        for (auto it = range.first; it != range.second; ++it)
+            if (it->second.tid == std::this_thread::get_id()) pick = it;  // the innermost of this thread
+        if (pick == range.second)
+        {
+            pick = range.first;
+            for (auto it = range.first; it != range.second; ++it)
+                if (it->second.t0 < pick->second.t0) pick = it;
+        }
+        const double dt = now() - pick->second.t0;
+        open_.erase(pick);
         add(name, dt);
         return dt;
     }
@@ -141,7 +153,12 @@ class TimeLogger
     }
     std::mutex                    mtx_;
     std::map<std::string, Stat>   stats_;
-    std::map<std::string, double> open_;
+    struct Open
+    {
+        std::thread::id tid;
+        double          t0;
+    };
+    std::multimap<std::string, Open> open_;
 };
 
 struct ProfilerEntry

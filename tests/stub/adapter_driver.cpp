@@ -12,6 +12,7 @@
 using mrpt::containers::yaml;
 extern "C" unsigned long fake_align_calls(void);
 extern "C" unsigned long fake_upload_calls(void);
+extern "C" unsigned long fake_last_call_max_iterations(void);
 
 static int g_fail = 0;
 #define CHECK(cond)                                                       \
@@ -95,6 +96,9 @@ int main()
     prm2.maxIterations = 50;
     icp->align(from, to, mrpt::math::TPose3D(), prm2, res);
     CHECK(res.quality == 1.0);
+    CHECK(fake_last_call_max_iterations() == 50);  // travelled with the call ...
+    CHECK(b200->contexts() == 1);                  // ... no second device object, no second upload
+    CHECK(b200->cachedClouds() == 2);
 
     // --- concurrent align on one shared object (h:167-172, cpp:711-729)
     {

@@ -116,6 +116,23 @@ int b200icp_align(b200icp_t* icp, const b200icp_cloud_t* from, const b200icp_clo
     fake_result(from, to, guess6, out);
     return B200ICP_OK;
 }
+void b200icp_call_params_of(const b200icp_params_t* p, b200icp_call_params_t* out)
+{
+    memset(out, 0, sizeof(*out));
+    out->max_iterations = p->max_iterations;
+    out->min_abs_step_trans = p->min_abs_step_trans, out->min_abs_step_rot = p->min_abs_step_rot;
+}
+static unsigned long g_last_call_max_iterations = 0;
+unsigned long        fake_last_call_max_iterations(void) { return g_last_call_max_iterations; }
+int b200icp_align_with(b200icp_t* icp, const b200icp_cloud_t* from, const b200icp_cloud_t* to,
+                       const double guess6[6], const b200icp_call_params_t* call, b200icp_result_t* out)
+{
+    (void)icp;
+    __atomic_add_fetch(&g_align_calls, 1, __ATOMIC_RELAXED);
+    if (call) g_last_call_max_iterations = call->max_iterations;
+    fake_result(from, to, guess6, out);
+    return B200ICP_OK;
+}
 int b200icp_align_batch(b200icp_t* icp, size_t n, const b200icp_cloud_t* const* from,
                         const b200icp_cloud_t* const* to, const double* guesses6, b200icp_result_t* out)
 {

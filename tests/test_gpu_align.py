@@ -100,3 +100,36 @@ def test_run_to_run_bit_reproducible(icp):
     g_a2, g_b2 = icp.upload(A), icp.upload(B)
     r2 = icp.align(g_a2, g_b2, np.zeros(6))
     assert np.array_equal(r1["pose"], r2["pose"]) and np.array_equal(r1["cov"], r2["cov"])
+
+
+def test_per_call_parameters_keep_the_objects_matchers(icp, oracle):
+    """icp->align(from, to, guess, in.icp_params, result) (LidarOdometry.cpp:869-871): the call's
+    mp2p_icp::Parameters (iteration budget, step tolerances) on the OBJECT's matchers / solvers / quality
+    evaluators -- b200icp_align_with equals the oracle run with those Parameters, and no second device
+    object is involved."""
+    from mola_fe_lidar_b200 import scene
+    A, B, _ = scene.make_pair_c1(seed=6, n=8000, sigma=0.01)
+    g_a, g_b = icp.upload(A), icp.upload(B)
+    full = icp.align(g_a, g_b, np.zeros(6))
+    assert full["n_iterations"] > 2
+    for kw in ({"max_iterations": 2}, {"min_abs_step_trans": 1e-2, "min_abs_step_rot": 1e-2}):
+        g = icp.align_with(g_a, g_b, np.zeros(6), **kw)
+        prm = oracle.default_params()
+        for k, v in kw.items():
+            setattr(prm, k, v)
+        o = oracle.icp_align(oracle.Cloud(A), oracle.Cloud(B), np.zeros(6), prm, kdtree=True)
+        _assert_same(g, o)
+        assert g["n_iterations"] < full["n_iterations"]
+    # the object's own parameters are untouched
+    again = icp.align(g_a, g_b, np.zeros(6))
+    assert np.array_equal(again["pose"], full["pose"]) and again["n_iterations"] == full["n_iterations"]
+
+
+def test_varying_cloud_sizes_back_to_back(icp, oracle):
+    """Real scans (and decimated ones) change their point count every frame: consecutive registrations of
+    clouds of different sizes on one ICP object stay correct whatever launch configuration is reused."""
+    from mola_fe_lidar_b200 import scene
+    for seed, n in ((11, 5000), (12, 5100), (13, 4700), (14, 9000), (15, 5000), (16, 300)):
+        A, B, _ = scene.make_pair_c1(seed=seed, n=n, sigma=0.005)
+        g, o = _run(icp, oracle, A, B, np.zeros(6))
+        _assert_same(g, o)

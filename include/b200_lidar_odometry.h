@@ -56,6 +56,15 @@ void b200lo_reset(b200lo_t* lo);
  * (asynchronous, with the reference's >10-queued drop rule). */
 int b200lo_on_new_observation(b200lo_t* lo, const char* sensor_label, double timestamp,
                               const float* x, const float* y, const float* z, size_t n);
+/* Same without the copy: the caller keeps x / y / z valid (pinned host memory gives asynchronous DMA) until
+ * the scan has been processed (b200lo_wait_idle, or b200lo_queue_length() == 0 and the next call returned).
+ * With `b200_prefetch_uploads` (default) the scan is uploaded and indexed on its own stream while the previous
+ * one is still being registered. */
+int b200lo_enqueue_observation(b200lo_t* lo, const char* sensor_label, double timestamp,
+                               const float* x, const float* y, const float* z, size_t n);
+/* scans waiting in the module's 1-thread pool: a harness feeding faster than real time throttles on it (the
+ * reference drops scans once more than 10 are queued, cpp:171-179) */
+size_t b200lo_queue_length(b200lo_t* lo);
 /* same, but processes the scan on the calling thread before returning; the
  * coordinates may live in pinned memory and are not copied */
 int b200lo_process_observation(b200lo_t* lo, const char* sensor_label, double timestamp,

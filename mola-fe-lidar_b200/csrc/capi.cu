@@ -108,6 +108,8 @@ extern "C" void b200icp_destroy(b200icp_t* icp)
         w->destroy();
         delete w;
     }
+    for (auto& sl : icp->slab_cache) cudaFree(sl.p);
+    for (auto e : icp->ready_events) cudaEventDestroy(e);
     {
         std::lock_guard<std::mutex> lk(icp->mtx);
         icp->drain_pending();
@@ -135,7 +137,7 @@ static int upload_common(b200icp_t* icp, const float* x, const float* y, const f
         return B200ICP_ERR_BAD_ARG;
     }
     *out = nullptr;
-    Lease L(icp);
+    Lease L(icp, /*upload=*/true);  // its own stream: overlaps the registration that is running
     if (!L.ws) return B200ICP_ERR_CUDA;
     b200icp_cloud* c = nullptr;
     if (int r = cloud_alloc(icp, L.ws, n, search_radius, &c)) return r;
@@ -190,19 +192,16 @@ extern "C" void b200icp_cloud_free(b200icp_cloud_t* c)
 {
     if (!c) return;
     cudaSetDevice(c->ctx->device);
+    // the index build is the last device work that touches the slab on the library's side; the registrations
+    // that read it have returned (the caller frees a cloud after its calls)
     if (c->ready) cudaEventSynchronize(c->ready);
     if (c->slab)
     {
-        Workspace* ws = c->ctx->acquire();
-        if (ws)
-        {
-            cudaFreeAsync(c->slab, ws->stream);
-            c->ctx->release(ws);
-        }
-        else
-            cudaFree(c->slab);
+        Workspace* ws = c->ctx->acquire(/*upload=*/true);
+        c->ctx->give_slab(c->slab, c->slab_bytes, ws ? ws->stream : nullptr);
+        if (ws) c->ctx->release(ws);
     }
-    if (c->ready) cudaEventDestroy(c->ready);
+    if (c->ready) c->ctx->give_ready_event(c->ready);
     delete c;
 }
 

@@ -301,21 +301,20 @@ int cloud_alloc(::b200icp* ctx, Workspace* ws, size_t n, float search_radius, b2
         c->bbox_enc = k.take<uint32_t>(8);
     };
     layout(cv);
-    cudaError_t e = cudaMallocAsync(&c->slab, cv.off, ws->stream);
-    if (e != cudaSuccess)
+    c->slab = ctx->take_slab(cv.off, &c->slab_bytes, ws->stream);  // recycled from a freed cloud, else the pool
+    if (!c->slab)
     {
-        set_error("cudaMallocAsync(%zu bytes) failed: %s", cv.off, cudaGetErrorString(e));
+        set_error("device allocation of %zu bytes for a cloud failed", cv.off);
         delete c;
-        return e == cudaErrorMemoryAllocation ? B200ICP_ERR_NOMEM : B200ICP_ERR_CUDA;
+        return B200ICP_ERR_NOMEM;
     }
-    c->slab_bytes = cv.off;
     Carver real(c->slab);
     layout(real);
-    e = cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming);
-    if (e != cudaSuccess)
+    c->ready = ctx->take_ready_event();
+    if (!c->ready)
     {
-        set_error("cudaEventCreate failed: %s", cudaGetErrorString(e));
-        cudaFreeAsync(c->slab, ws->stream);
+        set_error("cudaEventCreate failed");
+        ctx->give_slab(c->slab, c->slab_bytes, ws->stream);
         delete c;
         return B200ICP_ERR_CUDA;
     }

@@ -116,14 +116,15 @@ void make_dev_params(const b200icp_params_t& P, IcpDevParams& D)
 }
 }  // namespace b2
 
-b2::Workspace* b200icp::acquire()
+b2::Workspace* b200icp::acquire(bool upload)
 {
     {
         std::lock_guard<std::mutex> lk(mtx);
-        if (!free_ws.empty())
+        auto&                       pool = upload ? free_upload_ws : free_ws;
+        if (!pool.empty())
         {
-            auto* w = free_ws.back();
-            free_ws.pop_back();
+            auto* w = pool.back();
+            pool.pop_back();
             cudaSetDevice(device);
             return w;
         }
@@ -134,9 +135,99 @@ b2::Workspace* b200icp::acquire()
         delete w;
         return nullptr;
     }
+    w->upload = upload;
     std::lock_guard<std::mutex> lk(mtx);
     all_ws.push_back(w);
     return w;
+}
+
+// smallest cached slab that fits and is not more than twice too large; else a fresh allocation
+void* b200icp::take_slab(size_t need, size_t* got, cudaStream_t stream)
+{
+    {
+        std::lock_guard<std::mutex> lk(mtx);
+        int                         best = -1;
+        for (int i = 0; i < (int)slab_cache.size(); i++)
+            if (slab_cache[i].bytes >= need && slab_cache[i].bytes <= 2 * need &&
+                (best < 0 || slab_cache[i].bytes < slab_cache[best].bytes))
+                best = i;
+        if (best >= 0)
+        {
+            const Slab sl = slab_cache[best];
+            slab_cache.erase(slab_cache.begin() + best);
+            slab_cache_bytes -= sl.bytes;
+            *got = sl.bytes;
+            return sl.p;
+        }
+    }
+    // a miss goes to the device's stream-ordered pool (kept warm: release threshold = max, primed at create):
+    // a few microseconds, where cudaMalloc costs hundreds and serialises with running work
+    const size_t want = b2::align_up(need + need / 8, (size_t)1 << 20);  // room for the next, slightly larger scan
+    void*        p = nullptr;
+    if (cudaMallocAsync(&p, want, stream) != cudaSuccess)
+    {
+        cudaGetLastError();
+        std::vector<Slab> drop;
+        {
+            std::lock_guard<std::mutex> lk(mtx);
+            drop.swap(slab_cache);
+            slab_cache_bytes = 0;
+        }
+        for (auto& d : drop) cudaFreeAsync(d.p, stream);
+        if (cudaMallocAsync(&p, need, stream) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return nullptr;
+        }
+        *got = need;
+        return p;
+    }
+    *got = want;
+    return p;
+}
+
+void b200icp::give_slab(void* p, size_t bytes, cudaStream_t stream)
+{
+    constexpr size_t kMaxCached = 16;
+    constexpr size_t kMaxBytes = (size_t)2 << 30;
+    std::vector<Slab> drop;
+    {
+        std::lock_guard<std::mutex> lk(mtx);
+        slab_cache.push_back({p, bytes});
+        slab_cache_bytes += bytes;
+        while (slab_cache.size() > kMaxCached || slab_cache_bytes > kMaxBytes)
+        {   // oldest out
+            drop.push_back(slab_cache.front());
+            slab_cache_bytes -= slab_cache.front().bytes;
+            slab_cache.erase(slab_cache.begin());
+        }
+    }
+    for (auto& d : drop) cudaFreeAsync(d.p, stream);
+}
+
+cudaEvent_t b200icp::take_ready_event()
+{
+    {
+        std::lock_guard<std::mutex> lk(mtx);
+        if (!ready_events.empty())
+        {
+            cudaEvent_t e = ready_events.back();
+            ready_events.pop_back();
+            return e;
+        }
+    }
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    return e;
+}
+
+void b200icp::give_ready_event(cudaEvent_t e)
+{
+    std::lock_guard<std::mutex> lk(mtx);
+    if (ready_events.size() < 64)
+        ready_events.push_back(e);
+    else
+        cudaEventDestroy(e);
 }
 
 void b200icp::drain_pending()
@@ -161,5 +252,5 @@ void b200icp::release(b2::Workspace* ws)
     std::lock_guard<std::mutex> lk(mtx);
     prof.total_kernel_launches += ws->launches;
     ws->launches = 0;
-    free_ws.push_back(ws);
+    (ws->upload ? free_upload_ws : free_ws).push_back(ws);
 }

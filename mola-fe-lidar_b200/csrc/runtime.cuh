@@ -78,6 +78,7 @@ struct Workspace
     uint64_t     launches = 0;
     uint32_t*    d_flag = nullptr;  // 256 B of device memory / pinned memory for small status words
     uint32_t*    h_flag = nullptr;
+    bool         upload = false;    // belongs to the upload pool
 
     struct AlignGraph
     {
@@ -130,7 +131,23 @@ struct b200icp
     b2::IcpDevParams              D;
     std::mutex                         mtx;
     std::vector<b2::Workspace*>   free_ws;
+    std::vector<b2::Workspace*>   free_upload_ws;  // their streams carry cloud uploads / index builds only, so that
+                                                   // the next scan is indexed while a registration is running
     std::vector<b2::Workspace*>   all_ws;
+    // Cloud slabs and their "ready" events are recycled: a scan's cloud lives for two registrations, and a
+    // device allocation per scan costs more host time than the upload itself
+    struct Slab
+    {
+        void*  p;
+        size_t bytes;
+    };
+    std::vector<Slab>        slab_cache;
+    size_t                   slab_cache_bytes = 0;
+    std::vector<cudaEvent_t> ready_events;
+    void*                    take_slab(size_t need, size_t* got, cudaStream_t stream);  // null on failure
+    void                     give_slab(void* p, size_t bytes, cudaStream_t stream);
+    cudaEvent_t              take_ready_event();
+    void                     give_ready_event(cudaEvent_t e);
     bool                               profile_on = false;
     b200icp_profile_t                  prof;
     int                                sm_count = 148;
@@ -146,7 +163,7 @@ struct b200icp
     std::vector<cudaEvent_t>      event_pool;
     void                          drain_pending();  // call with mtx held
 
-    b2::Workspace* acquire();
+    b2::Workspace* acquire(bool upload = false);
     void                release(b2::Workspace* ws);
 };
 
@@ -189,7 +206,7 @@ struct Lease
 {
     ::b200icp* ctx;
     Workspace* ws;
-    explicit Lease(::b200icp* c) : ctx(c), ws(c->acquire()) {}
+    explicit Lease(::b200icp* c, bool upload = false) : ctx(c), ws(c->acquire(upload)) {}
     ~Lease()
     {
         if (ws) ctx->release(ws);

@@ -76,6 +76,7 @@ LidarOdometry::LidarOdometry() = default;
 
 LidarOdometry::~LidarOdometry()
 {
+    worker_pool_prefetch_.clear();
     worker_pool_.clear();
     worker_pool_past_KFs_.clear();
     release_icp_objects();
@@ -142,6 +143,7 @@ void LidarOdometry::initialize(const Yaml& c)
     cfg.load_opt("b200_device", params_.device);
     cfg.load_opt("b200_extra_edge_checks", params_.extra_edge_checks);
     cfg.load_opt("b200_kf_store_budget_mb", params_.kf_store_budget_mb);
+    cfg.load_opt("b200_prefetch_uploads", params_.prefetch_uploads);
     {
         unsigned int seed = (unsigned int)params_.montecarlo_seed;
         cfg.load_opt("b200_montecarlo_seed", seed);
@@ -198,12 +200,15 @@ void LidarOdometry::spinOnce() { ProfilerEntry tleg(profiler_, "spinOnce"); }  /
 
 void LidarOdometry::reset()  // cpp:160
 {
+    worker_pool_prefetch_.waitIdle();
+    prefetch_last_tim_ = -1.0;
     std::lock_guard<std::mutex> lk(state_mtx_);
     state_ = MethodState();
 }
 
 void LidarOdometry::waitIdle()
 {
+    worker_pool_prefetch_.waitIdle();
     worker_pool_.waitIdle();
     worker_pool_past_KFs_.waitIdle();
 }
@@ -226,6 +231,31 @@ void LidarOdometry::onNewObservation(CObservation::Ptr& o)
     }
     profiler_.enter("delay_onNewObs_to_process");
     CObservation::Ptr obs = o;
+    if (params_.prefetch_uploads)
+    {
+        // stage 1 on its own thread and CUDA stream: the scan is on the device, indexed, by the time the
+        // 1-thread pool gets to it.  The time gate of cpp:201-212 is a function of the timestamps alone, so the
+        // prefetch thread replays it and does not upload scans that will be skipped.
+        auto prom = std::make_shared<std::promise<DeviceCloud::Ptr>>();
+        obs->prefetched = prom->get_future().share();
+        worker_pool_prefetch_.enqueue([this, obs, prom]() {
+            try
+            {
+                const double t = obs->timestamp;
+                if (prefetch_last_tim_ >= 0 && (t - prefetch_last_tim_) < params_.min_time_between_scans)
+                {
+                    prom->set_value(nullptr);
+                    return;
+                }
+                prefetch_last_tim_ = t;
+                prom->set_value(make_cloud(*obs));
+            }
+            catch (...)
+            {
+                prom->set_exception(std::current_exception());
+            }
+        });
+    }
     worker_pool_.enqueue([this, obs]() mutable { doProcessNewObservation(obs); });
 }
 
@@ -269,8 +299,11 @@ void LidarOdometry::doProcessNewObservation(CObservation::Ptr& o)
             return;
         }
 
-        // Extract points from observation + filter/segment (cpp:214-226)
-        DeviceCloud::Ptr this_obs_points = make_cloud(*o);
+        // Extract points from observation + filter/segment (cpp:214-226): already under way on the prefetch
+        // thread when the scan came through onNewObservation
+        DeviceCloud::Ptr this_obs_points;
+        if (o->prefetched.valid()) this_obs_points = o->prefetched.get();
+        if (!this_obs_points) this_obs_points = make_cloud(*o);
 
         profiler_.enter("doProcessNewObservation.2.copy_vars");
         // Store for next step (cpp:230-234)

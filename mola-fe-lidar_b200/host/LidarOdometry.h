@@ -128,6 +128,11 @@ class LidarOdometry : public FrontEndBase
          *  (cpp:493-508), so that every processed scan costs exactly one
          *  consecutive-scan registration (the unit bench.py times) */
         bool extra_edge_checks{true};
+        /** additive key `b200_prefetch_uploads` (default true): onNewObservation hands the scan to a second
+         *  1-thread pool that uploads and indexes it on its own CUDA stream while the previous scan is still
+         *  being registered; doProcessNewObservation then only waits for that cloud.  Same clouds, same
+         *  order, same results -- the reference does both stages on its one worker thread (cpp:190-226). */
+        bool prefetch_uploads{true};
         /** additive key `b200_kf_store_budget_mb`: HBM the key-frame clouds may hold together; beyond it the
          *  least recently used ones are spilled to host memory (0 = no limit, the default) */
         double kf_store_budget_mb{0.0};
@@ -190,6 +195,8 @@ class LidarOdometry : public FrontEndBase
 
     /** blocks until both worker pools are idle (harness helper) */
     void waitIdle();
+    /** scans waiting in the 1-thread pool (what the drop rule of cpp:171-179 looks at) */
+    size_t queueLength() { return worker_pool_.pendingTasks(); }
     WorldModel::Ptr worldmodel() { return worldmodel_; }
     void            setWorldModel(WorldModel::Ptr w) { worldmodel_ = std::move(w); }
     TimeLogger      profiler_;
@@ -202,6 +209,8 @@ class LidarOdometry : public FrontEndBase
    private:
     WorkerThreadsPool worker_pool_{1};
     WorkerThreadsPool worker_pool_past_KFs_{1};
+    WorkerThreadsPool worker_pool_prefetch_{1};  // observation -> device cloud, ahead of worker_pool_
+    double            prefetch_last_tim_{-1.0};  // the time gate of cpp:201-212, replayed by the prefetch thread
 
     MethodState     state_;
     WorldModel::Ptr worldmodel_;

@@ -115,6 +115,25 @@ extern "C" int b200lo_on_new_observation(b200lo_t* lo, const char* label, double
     }
 }
 
+extern "C" int b200lo_enqueue_observation(b200lo_t* lo, const char* label, double t, const float* x,
+                                          const float* y, const float* z, size_t n)
+{
+    if (!lo || (n && (!x || !y || !z))) return -1;
+    try
+    {
+        auto o = make_obs(label, t, x, y, z, n, false);  // the caller keeps the buffers alive until processed
+        lo->lo->onNewObservation(o);
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        g_lo_err = e.what();
+        return -2;
+    }
+}
+
+extern "C" size_t b200lo_queue_length(b200lo_t* lo) { return lo ? lo->lo->queueLength() : 0; }
+
 extern "C" int b200lo_process_observation(b200lo_t* lo, const char* label, double t, const float* x,
                                           const float* y, const float* z, size_t n)
 {

@@ -45,12 +45,16 @@ struct TTwist3D
 
 /** mrpt::obs::CObservationPointCloud reduced to what the path reads: label,
  *  timestamp and the SoA float buffers of its CPointsMap. */
+struct DeviceCloud;
 struct CObservation
 {
     using Ptr = std::shared_ptr<CObservation>;
     std::string        sensorLabel;
     double             timestamp = 0;  // seconds
     std::vector<float> x, y, z;
+    /** set by LidarOdometry::onNewObservation when uploads are prefetched: the scan's device cloud, being
+     *  uploaded and indexed on its own stream while the previous scan is still being registered */
+    std::shared_future<std::shared_ptr<DeviceCloud>> prefetched;
     /** non-null => coordinates are already in pinned / device-visible host memory */
     const float *px = nullptr, *py = nullptr, *pz = nullptr;
     size_t       n = 0;

@@ -4,6 +4,7 @@ reference's YAML parameter files, feed observations, read the state back.
 No CPU fallback: creation fails when the CUDA library cannot reach a B200."""
 import ctypes as C
 import os
+import time
 
 import numpy as np
 
@@ -15,7 +16,8 @@ PARAMS_DIR = os.path.join(PKG_DIR, "params")
 
 EXPORTS = [
     "b200lo_last_error", "b200lo_create", "b200lo_destroy", "b200lo_reset",
-    "b200lo_on_new_observation", "b200lo_process_observation", "b200lo_spin_once",
+    "b200lo_on_new_observation", "b200lo_enqueue_observation", "b200lo_queue_length",
+    "b200lo_process_observation", "b200lo_spin_once",
     "b200lo_wait_idle", "b200lo_get_state", "b200lo_get_factors", "b200lo_dump_params",
     "b200lo_dump_profile", "b200lo_icp_handle",
 ]
@@ -61,8 +63,10 @@ def lib():
     L.b200lo_destroy.restype = None
     L.b200lo_reset.argtypes = [vp]
     L.b200lo_reset.restype = None
-    for name in ("b200lo_on_new_observation", "b200lo_process_observation"):
+    for name in ("b200lo_on_new_observation", "b200lo_process_observation", "b200lo_enqueue_observation"):
         getattr(L, name).argtypes = [vp, C.c_char_p, C.c_double, vp, vp, vp, C.c_size_t]
+    L.b200lo_queue_length.argtypes = [vp]
+    L.b200lo_queue_length.restype = C.c_size_t
     L.b200lo_spin_once.argtypes = [vp]
     L.b200lo_spin_once.restype = None
     L.b200lo_wait_idle.argtypes = [vp]
@@ -122,6 +126,17 @@ class LidarOdometry:
         rc = f(self.h, label.encode(), timestamp, px, py, pz, n)
         if rc != 0:
             raise capi.B200IcpError(f"onNewObservation failed ({rc}): {lib().b200lo_last_error().decode()}")
+
+    def enqueueObservationSoA(self, px, py, pz, n, timestamp, label="lidar", max_queued=4):
+        """Asynchronous feed without a copy (b200lo_enqueue_observation): the buffers must stay valid until the
+        scan has been processed.  Waits while more than `max_queued` scans are pending, so that a harness feeding
+        faster than real time never triggers the >10-queued drop rule (LidarOdometry.cpp:171-179)."""
+        L = lib()
+        while L.b200lo_queue_length(self.h) > max_queued:
+            time.sleep(20e-6)
+        rc = L.b200lo_enqueue_observation(self.h, label.encode(), timestamp, px, py, pz, n)
+        if rc != 0:
+            raise capi.B200IcpError(f"enqueueObservation failed ({rc}): {L.b200lo_last_error().decode()}")
 
     def spinOnce(self):
         lib().b200lo_spin_once(self.h)

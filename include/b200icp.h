@@ -157,6 +157,11 @@ int b200icp_device(const b200icp_t* icp);
  * kd-tree build).  search_radius <= 0 => the ICP object's matcher threshold. */
 int b200icp_cloud_upload(b200icp_t* icp, const float* x, const float* y, const float* z,
                          size_t n, float search_radius, b200icp_cloud_t** out);
+/* Coordinates only, no search index: the input of a filter stage (b200icp_voxel_decimate) whose OUTPUT is what
+ * gets registered -- apply_generators followed by apply_filter_pipeline, LidarOdometry.cpp:215-224.  Such a cloud
+ * is refused (B200ICP_ERR_BAD_ARG) as a side of b200icp_knn / _match / _align. */
+int b200icp_cloud_upload_raw(b200icp_t* icp, const float* x, const float* y, const float* z, size_t n,
+                             b200icp_cloud_t** out);
 /* Same from DEVICE pointers (inputs already resident in HBM). */
 int b200icp_cloud_from_device(b200icp_t* icp, const float* dx, const float* dy, const float* dz,
                               size_t n, float search_radius, b200icp_cloud_t** out);

@@ -104,7 +104,8 @@ class Profile(C.Structure):
 EXPORTS = [
     "b200icp_last_error", "b200icp_device_count", "b200icp_default_params",
     "b200icp_params_from_yaml", "b200icp_create", "b200icp_create_from_yaml", "b200icp_destroy",
-    "b200icp_get_params", "b200icp_device", "b200icp_cloud_upload", "b200icp_cloud_from_device",
+    "b200icp_get_params", "b200icp_device", "b200icp_cloud_upload", "b200icp_cloud_upload_raw",
+    "b200icp_cloud_from_device",
     "b200icp_cloud_free", "b200icp_cloud_size", "b200icp_cloud_device_bytes", "b200icp_cloud_download",
     "b200icp_voxel_decimate", "b200icp_knn", "b200icp_knn_keys_device", "b200icp_merge_keys_device",
     "b200icp_knn_keys_scatter", "b200icp_peer_alloc", "b200icp_peer_free", "b200icp_peer_open",
@@ -139,6 +140,7 @@ def lib():
     L.b200icp_get_params.argtypes = [vp, C.POINTER(Params)]
     L.b200icp_device.argtypes = [vp]
     L.b200icp_cloud_upload.argtypes = [vp, vp, vp, vp, C.c_size_t, C.c_float, C.POINTER(vp)]
+    L.b200icp_cloud_upload_raw.argtypes = [vp, vp, vp, vp, C.c_size_t, C.POINTER(vp)]
     L.b200icp_cloud_from_device.argtypes = [vp, vp, vp, vp, C.c_size_t, C.c_float, C.POINTER(vp)]
     L.b200icp_cloud_free.argtypes = [vp]
     L.b200icp_cloud_free.restype = None
@@ -269,6 +271,14 @@ class ICP:
         h = C.c_void_p()
         _check(lib().b200icp_cloud_upload(self.h, x.ctypes.data, y.ctypes.data, z.ctypes.data, n,
                                           search_radius, C.byref(h)))
+        return Cloud(self, h)
+
+    def upload_raw(self, xyz):
+        """Coordinates only, no search index (b200icp_cloud_upload_raw): the input of voxel_decimate."""
+        xyz = np.asarray(xyz, dtype=np.float32).reshape(-1, 3)
+        x, y, z = (np.ascontiguousarray(xyz[:, i]) for i in range(3))
+        h = C.c_void_p()
+        _check(lib().b200icp_cloud_upload_raw(self.h, x.ctypes.data, y.ctypes.data, z.ctypes.data, len(x), C.byref(h)))
         return Cloud(self, h)
 
     def upload_ptrs(self, px, py, pz, n, search_radius=0.0):

@@ -635,7 +635,7 @@ __device__ __forceinline__ bool deliver_chunk(JobDev& J, uint32_t chunk, uint32_
     sum_records(fb.gpartials + (size_t)J.group_base * kNumMoments, n_groups, idx, v);
     if (lane == 0) J.dbg_tail[0] = (uint32_t)(clock64() - t0);
 #pragma unroll
-    for (int i = 0; i < 6; i++) sS[idx[i]] = v[i], J.M[idx[i]] = v[i];
+    for (int i = 0; i < 6; i++) J.Mprev[idx[i]] = J.M[idx[i]], sS[idx[i]] = v[i], J.M[idx[i]] = v[i];
     __syncwarp();
     return true;
 }
@@ -933,8 +933,23 @@ __global__ void __launch_bounds__(kChunk)
 // End of one outer iteration of ICP::align (row G / A.7), one thread: adopt
 // the solver's pose, test the step delta = log(Tprev^-1 * Tnew) split into
 // (xyz, rot), update the job's status.
-__device__ void finish_outer_iteration(JobDev& J, const Pose& Tn, uint32_t npair, uint32_t inner,
-                                       const IcpDevParams& P, uint32_t* n_active)
+// One outer iteration maps the pose to the next pose, pose' = f(pose): the search is exact whatever bounds it,
+// the moments are summed in an order fixed by the data, the solver is deterministic -- f is a pure function
+// of the pose (as long as the matcher is active at every iteration).  ICP on coarse clouds often ends in a
+// 2-cycle between two pairing sets, which the reference's loop runs up to maxIterations: 100 iterations that
+// alternate between two poses.  Inside such a cycle the pairing sets repeat exactly and each solve lands on the
+// minimiser of the same quadratic, so the poses repeat up to the rounding of the Gauss-Newton iterates
+// (~1e-14); they repeat BITWISE only by luck.  The cycle is recognised when, on two consecutive iterations,
+// the new pose equals the pose of two iterations before within 1e-11 (m / rad; `detect_cycles` 1: bitwise
+// only) and the pairing count equals the one of two iterations before.  The rest of the run is then known: poses,
+// moments and pairing counts alternate, no step is ever below the tolerances (these were not), the loop ends
+// with MaxIterations in the state its parity gives.  The job jumps there: same iteration count, termination
+// reason and pairing count as running it out, pose within 1e-11 of it (the stated tolerance is 1e-5 m / 1e-6
+// rad; B200ICP_CYCLE=0 runs every iteration).
+// Returns 0: nothing special; 1: fast-forwarded, state as is; 2: fast-forwarded, and the caller must swap the
+// moments with the previous ones (done by the whole warp).
+__device__ int finish_outer_iteration(JobDev& J, const Pose& Tn, uint32_t npair, uint32_t inner,
+                                      const IcpDevParams& P, uint32_t* n_active, bool allow_cycle)
 {
     Pose T0, dT;
     for (int i = 0; i < 9; i++) T0.R[i] = J.R[i];
@@ -944,27 +959,55 @@ __device__ void finish_outer_iteration(JobDev& J, const Pose& Tn, uint32_t npair
     se3_log(dT, d);
     const double dxyz = sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
     const double drot = sqrt((d[3] * d[3] + d[4] * d[4]) + d[5] * d[5]);
+    bool same_as_two_back = allow_cycle && P.detect_cycles && J.iter >= 2 && P.run_from_iteration == 0 &&
+                            P.run_up_to_iteration == 0 && npair == J.npair_prev;  // npair_prev: two iterations back
+    if (same_as_two_back)
+    {
+        const double tol = (P.detect_cycles >= 2) ? 1e-11 : 0.0;
+        for (int i = 0; i < 9; i++) same_as_two_back = same_as_two_back && (fabs(Tn.R[i] - J.Rprev[i]) <= tol);
+        for (int i = 0; i < 3; i++) same_as_two_back = same_as_two_back && (fabs(Tn.t[i] - J.tprev[i]) <= tol);
+    }
+    J.cycle_hits = same_as_two_back ? J.cycle_hits + 1 : 0;
+    same_as_two_back = J.cycle_hits >= 2;
+    const uint32_t npair_before = J.n_pairings, inner_before = J.inner_prev;
     for (int i = 0; i < 9; i++) J.Rprev[i] = T0.R[i], J.R[i] = Tn.R[i];
     for (int i = 0; i < 3; i++) J.tprev[i] = T0.t[i], J.t[i] = Tn.t[i];
+    J.npair_prev = npair_before;
     J.n_pairings = npair;
     J.inner_iters_total += inner;
+    J.inner_prev = inner;
     if (dxyz < P.min_abs_step_trans && drot < P.min_abs_step_rot)
     {
         J.status = 1;
         J.term_reason = B200ICP_TERM_STALLED;
         atomicSub(n_active, 1u);
+        return 0;
     }
-    else
+    const uint32_t it = J.iter + 1;  // iterations completed
+    J.iter = it;
+    if (it >= P.max_iterations)
     {
-        const uint32_t it = J.iter + 1;
-        J.iter = it;
-        if (it >= P.max_iterations)
-        {
-            J.status = 1;
-            J.term_reason = B200ICP_TERM_MAX_ITERATIONS;
-            atomicSub(n_active, 1u);
-        }
+        J.status = 1;
+        J.term_reason = B200ICP_TERM_MAX_ITERATIONS;
+        atomicSub(n_active, 1u);
+        return 0;
     }
+    if (!same_as_two_back) return 0;
+    // period 2 from here on: `left` more iterations would run; an even number leaves this state, an odd number
+    // the one of the previous iteration (pose_i, moments and pairings of iteration i - 1)
+    const uint32_t left = P.max_iterations - it;
+    J.cycle_at = it;
+    J.iter = P.max_iterations;
+    J.status = 1;
+    J.term_reason = B200ICP_TERM_MAX_ITERATIONS;
+    J.inner_iters_total += (left / 2) * (inner + inner_before) + ((left & 1u) ? inner_before : 0u);
+    atomicSub(n_active, 1u);
+    if ((left & 1u) == 0) return 1;
+    for (int i = 0; i < 9; i++) J.R[i] = T0.R[i], J.Rprev[i] = Tn.R[i];
+    for (int i = 0; i < 3; i++) J.t[i] = T0.t[i], J.tprev[i] = Tn.t[i];
+    J.n_pairings = npair_before;
+    J.npair_prev = npair;
+    return 2;
 }
 
 // optimal_tf_gauss_newton on the reduced moments (A.6) + the end of the outer
@@ -1098,9 +1141,16 @@ __device__ void solve_job_warp(JobDev& J, SolveSmem& ss, const IcpDevParams& P, 
         Pose Tn;
         for (int i = 0; i < 9; i++) Tn.R[i] = ss.R[i];
         for (int i = 0; i < 3; i++) Tn.t[i] = ss.t[i];
-        finish_outer_iteration(J, Tn, npair, inner, P, n_active);
+        ss.stop = finish_outer_iteration(J, Tn, npair, inner, P, n_active, true);
         J.dbg_tail[1] = (uint32_t)(t_fin - t_gn), J.dbg_tail[2] = (uint32_t)(clock64() - t_fin), J.dbg_tail[3] = inner;
     }
+    __syncwarp();
+    if (ss.stop == 2)
+        for (int i = lane; i < kNumMoments; i += 32)
+        {   // the run ends one iteration "earlier" in the cycle: its moments are the previous ones
+            const double m = J.M[i];
+            J.M[i] = J.Mprev[i], J.Mprev[i] = m;
+        }
 }
 
 // ------------------------------------------------------------ Horn (row N)
@@ -1263,7 +1313,7 @@ __global__ void __launch_bounds__(kHornSolveThreads)
     double Rp[3];
     mat3_vec(Tn.R, pc, Rp);
     for (int d = 0; d < 3; d++) Tn.t[d] = qc[d] - Rp[d];
-    finish_outer_iteration(J, Tn, npair, 1u, P, n_active);
+    finish_outer_iteration(J, Tn, npair, 1u, P, n_active, false);
 }
 
 // --------------------------------------------------------------- covariance
@@ -1381,6 +1431,12 @@ __global__ void __launch_bounds__(256)
 // =========================================================== host orchestration
 static int wait_cloud(Workspace* ws, const b200icp_cloud* c)
 {
+    if (!c->indexed)
+    {
+        set_error("this cloud holds coordinates only (b200icp_cloud_upload_raw): it can feed b200icp_voxel_decimate, "
+                  "not a search or a registration");
+        return B200ICP_ERR_BAD_ARG;
+    }
     B2_CUDA_TRY(cudaStreamWaitEvent(ws->stream, c->ready, 0));
     return B200ICP_OK;
 }
@@ -1712,7 +1768,15 @@ static int run_wave(::b200icp* ctx, Workspace* ws, const IcpDevParams& D, size_t
     };
     const uint32_t kBatch = 4;
     const bool     predict = (n == 1) && ctx->expected_runs.load() > 0;
-    const uint32_t first = predict ? (uint32_t)std::min(std::max(ctx->expected_runs.load() + 1, 2), 24) : kBatch;
+    // one more than the previous registration needed, rounded up to a few fixed sizes: every distinct size is
+    // a graph of its own to instantiate (milliseconds), an iteration enqueued in vain costs two empty launches
+    auto first_bucket = [](int runs) -> uint32_t {
+        static const int sizes[] = {3, 4, 5, 6, 8, 10, 12, 16, 20, 24};
+        for (int sz : sizes)
+            if (runs <= sz) return (uint32_t)sz;
+        return 24u;
+    };
+    const uint32_t first = predict ? first_bucket(ctx->expected_runs.load() + 1) : kBatch;
     uint32_t       enq = 0, batch = 0;
     bool           finished = false;
 

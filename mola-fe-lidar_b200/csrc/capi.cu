@@ -129,7 +129,7 @@ extern "C" int b200icp_get_params(const b200icp_t* icp, b200icp_params_t* out)
 extern "C" int b200icp_device(const b200icp_t* icp) { return icp ? icp->device : -1; }
 
 static int upload_common(b200icp_t* icp, const float* x, const float* y, const float* z, size_t n,
-                         float search_radius, cudaMemcpyKind kind, b200icp_cloud_t** out)
+                         float search_radius, cudaMemcpyKind kind, b200icp_cloud_t** out, bool coords_only = false)
 {
     if (!icp || !out || (n && (!x || !y || !z)))
     {
@@ -140,7 +140,7 @@ static int upload_common(b200icp_t* icp, const float* x, const float* y, const f
     Lease L(icp, /*upload=*/true);  // its own stream: overlaps the registration that is running
     if (!L.ws) return B200ICP_ERR_CUDA;
     b200icp_cloud* c = nullptr;
-    if (int r = cloud_alloc(icp, L.ws, n, search_radius, &c)) return r;
+    if (int r = cloud_alloc(icp, L.ws, n, search_radius, &c, 0.f, coords_only)) return r;
     cudaStream_t s = L.ws->stream;
     if (n)
     {
@@ -179,6 +179,12 @@ extern "C" int b200icp_cloud_upload(b200icp_t* icp, const float* x, const float*
                                     size_t n, float search_radius, b200icp_cloud_t** out)
 {
     return upload_common(icp, x, y, z, n, search_radius, cudaMemcpyHostToDevice, out);
+}
+
+extern "C" int b200icp_cloud_upload_raw(b200icp_t* icp, const float* x, const float* y, const float* z,
+                                        size_t n, b200icp_cloud_t** out)
+{
+    return upload_common(icp, x, y, z, n, 0.f, cudaMemcpyHostToDevice, out, /*coords_only=*/true);
 }
 
 extern "C" int b200icp_cloud_from_device(b200icp_t* icp, const float* dx, const float* dy,

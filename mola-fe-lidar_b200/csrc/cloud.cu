@@ -266,7 +266,8 @@ __global__ void fine_publish_kernel(const unsigned long long* __restrict__ skeys
     atomicOr(mask, 1ull << (uint32_t)(fine_of_key(key) & 63ull));
 }
 
-int cloud_alloc(::b200icp* ctx, Workspace* ws, size_t n, float search_radius, b200icp_cloud** out)
+int cloud_alloc(::b200icp* ctx, Workspace* ws, size_t n, float search_radius, b200icp_cloud** out, float min_cell,
+                bool coords_only)
 {
     if (n >= 0x7FFFFFFFull)
     {
@@ -278,9 +279,14 @@ int cloud_alloc(::b200icp* ctx, Workspace* ws, size_t n, float search_radius, b2
     c->n = n;
     float radius = search_radius > 0 ? search_radius : (float)ctx->P.distance_threshold;
     if (!(radius > 0) || !std::isfinite(radius)) radius = 1.0f;
+    // block edge: the search radius (27 blocks always cover it), or more when the caller knows the points are far
+    // apart (one point per voxel after decimation): with fine cells much smaller than the point spacing the shell
+    // walk would cross mostly empty cells -- up to 4 x 4 x 4 fine cells of the radius' size
     c->cell_req = radius * 1.002f;
+    if (min_cell > 0.25f * c->cell_req) c->cell_req = 4.0f * std::min(min_cell, c->cell_req);
+    c->indexed = !coords_only;
     uint32_t cap = 1024;
-    while (cap < 2 * n) cap <<= 1;
+    while (!coords_only && cap < 2 * n) cap <<= 1;
     c->hcap = cap;
     uint32_t lg = 0;
     while ((1u << lg) < cap) lg++;
@@ -289,6 +295,7 @@ int cloud_alloc(::b200icp* ctx, Workspace* ws, size_t n, float search_radius, b2
     Carver cv(nullptr);
     auto layout = [&](Carver& k) {
         c->dx = k.take<float>(nn), c->dy = k.take<float>(nn), c->dz = k.take<float>(nn);
+        if (coords_only) return;
         c->pts = k.take<float4>(nn);
         c->gbox = k.take<float4>(2 * ((nn + kGroup - 1) / kGroup));
         c->rank = k.take<uint32_t>(nn);
@@ -325,6 +332,11 @@ int cloud_alloc(::b200icp* ctx, Workspace* ws, size_t n, float search_radius, b2
 int cloud_build_index(::b200icp* ctx, Workspace* ws, b200icp_cloud* c)
 {
     cudaStream_t   s = ws->stream;
+    if (!c->indexed)
+    {   // coordinates only (the input of a filter stage): ready as soon as the copy is
+        B2_CUDA_TRY(cudaEventRecord(c->ready, s));
+        return B200ICP_OK;
+    }
     const uint32_t n = (uint32_t)c->n;
     const bool     prof = ctx->profile_on;
     cudaEvent_t    pe0 = nullptr, pe1 = nullptr;

@@ -78,6 +78,7 @@ struct JobDev
     double   R[9], t[3];          // current solution (to wrt from)
     double   Rprev[9], tprev[3];  // solution of the previous outer iteration
     double   M[kNumMoments];      // reduced moments of the last matcher run
+    double   Mprev[kNumMoments];  // ... and of the one before (period-2 fast-forward, align.cu)
     double   cov[36];
     uint32_t iter;         // outer iterations completed
     uint32_t status;       // 0 running, 1 finished
@@ -94,6 +95,10 @@ struct JobDev
     uint32_t chunk_base;   // first chunk partial / first group partial + ticket of this job in the launch's
     uint32_t group_base;   //   fit buffers (align.cu, "chunk partials")
     uint32_t groups_done;  // arrival counter of the job's group reductions; zero between launches
+    uint32_t npair_prev;   // n_pairings / inner iterations of the previous outer iteration
+    uint32_t inner_prev;
+    uint32_t cycle_hits;   // consecutive iterations whose pose repeated the pose of two iterations before
+    uint32_t cycle_at;     // outer iteration at which a period-2 cycle was recognised (0: none)
     uint32_t dbg_tail[4];  // development probe (last outer iteration): cycles of the final moment sum, of the
                            // Gauss-Newton loop, of the end-of-iteration step; inner iterations
 };
@@ -121,6 +126,7 @@ struct IcpDevParams
     double   scale_outlier_threshold;
     int32_t  use_robust_kernel;
     double   robust_kernel_param, robust_kernel_scale;
+    uint32_t detect_cycles;  // period-2 fast-forward: 0 off, 1 bitwise repeats only, 2 repeats within 1e-11 (default)
 };
 
 // One pairing as the closed-form (Horn) solver consumes it: the global-side

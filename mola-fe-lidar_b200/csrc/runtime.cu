@@ -1,7 +1,9 @@
 // runtime.cu -- context / workspace pool / error string (host side).
 #include "runtime.cuh"
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace b2
@@ -113,6 +115,8 @@ void make_dev_params(const b200icp_params_t& P, IcpDevParams& D)
     D.use_robust_kernel = P.use_robust_kernel;
     D.robust_kernel_param = P.robust_kernel_param;
     D.robust_kernel_scale = P.robust_kernel_scale;
+    const char* cyc = getenv("B200ICP_CYCLE");
+    D.detect_cycles = cyc ? (uint32_t)std::max(0, std::min(2, atoi(cyc))) : 2u;
 }
 }  // namespace b2
 

@@ -186,6 +186,7 @@ struct b200icp_cloud
     uint32_t* bbox_enc = nullptr;  // 6 order-encoded floats
     uint32_t  hcap = 0, hshift = 0;
     float     cell_req = 0;
+    bool      indexed = true;  // false: coordinates only (b200icp_cloud_upload_raw), not usable as a search side
     cudaEvent_t ready = nullptr;
 
     b2::CloudView view() const
@@ -213,7 +214,8 @@ struct Lease
     }
 };
 
-int cloud_alloc(::b200icp* ctx, Workspace* ws, size_t n, float search_radius, b200icp_cloud** out);
+int cloud_alloc(::b200icp* ctx, Workspace* ws, size_t n, float search_radius, b200icp_cloud** out,
+                float min_cell = 0.f, bool coords_only = false);
 int cloud_build_index(::b200icp* ctx, Workspace* ws, b200icp_cloud* c);
 
 int run_align_batch(::b200icp* ctx, size_t n, const b200icp_cloud* const* from,

@@ -206,7 +206,8 @@ int run_voxel(::b200icp* ctx, const b200icp_cloud* in, float resolution, int use
         }
     }
     b200icp_cloud* c = nullptr;
-    if (int r = cloud_alloc(ctx, ws, m, search_radius, &c)) return r;
+    // one point per voxel: neighbours are about a voxel apart, the index cells follow (never below the default)
+    if (int r = cloud_alloc(ctx, ws, m, search_radius, &c, 0.7f * resolution)) return r;
     if (m)
     {
         cudaError_t e = cudaMemcpyAsync(c->dx, ox, m * sizeof(float), cudaMemcpyDeviceToDevice, s);

@@ -264,14 +264,19 @@ DeviceCloud::Ptr LidarOdometry::make_cloud(const CObservation& o)
 {
     b200icp_t*       ctx = params_.icp.at(AlignKind::LidarOdometry).icp;
     b200icp_cloud_t* raw = nullptr;
-    {   // observation -> device cloud + search index (apply_generators, cpp:215-217)
+    const bool       filtered = params_.voxel_decimation_resolution > 0;
+    {   // observation -> device cloud (apply_generators, cpp:215-217); the search index is built for the cloud
+        // that gets registered: this one, or the output of the filter stage below
         ProfilerEntry tle0(profiler_, "doProcessNewObservation.0.upload_and_index");
-        check_rc(b200icp_cloud_upload(ctx, o.xs(), o.ys(), o.zs(), o.size(), cloud_search_radius_, &raw),
-                 "b200icp_cloud_upload");
+        if (filtered)
+            check_rc(b200icp_cloud_upload_raw(ctx, o.xs(), o.ys(), o.zs(), o.size(), &raw), "b200icp_cloud_upload_raw");
+        else
+            check_rc(b200icp_cloud_upload(ctx, o.xs(), o.ys(), o.zs(), o.size(), cloud_search_radius_, &raw),
+                     "b200icp_cloud_upload");
     }
     auto              raw_ptr = std::make_shared<DeviceCloud>(raw, ctx, cloud_search_radius_);
     ProfilerEntry     tle1(profiler_, "doProcessNewObservation.1.filter_pointclouds");
-    if (params_.voxel_decimation_resolution > 0)
+    if (filtered)
     {
         b200icp_cloud_t* dec = nullptr;
         check_rc(b200icp_voxel_decimate(ctx, raw, (float)params_.voxel_decimation_resolution,

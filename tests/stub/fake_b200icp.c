@@ -70,6 +70,11 @@ int b200icp_match(b200icp_t* icp, const b200icp_cloud_t* from_global, const b200
     if (n_pairings) *n_pairings = np;
     return B200ICP_OK;
 }
+int b200icp_cloud_upload_raw(b200icp_t* icp, const float* x, const float* y, const float* z, size_t n,
+                             b200icp_cloud_t** out)
+{
+    return b200icp_cloud_upload(icp, x, y, z, n, 0.f, out);
+}
 void   b200icp_cloud_free(b200icp_cloud_t* c) { free(c); }
 size_t b200icp_cloud_size(const b200icp_cloud_t* c) { return c ? c->n : 0; }
 size_t b200icp_cloud_device_bytes(const b200icp_cloud_t* c) { return c ? 100 * c->n : 0; }

@@ -133,3 +133,61 @@ def test_varying_cloud_sizes_back_to_back(icp, oracle):
         A, B, _ = scene.make_pair_c1(seed=seed, n=n, sigma=0.005)
         g, o = _run(icp, oracle, A, B, np.zeros(6))
         _assert_same(g, o)
+
+
+def test_period_two_fast_forward_matches_the_full_loop(capi, oracle):
+    """Registrations of coarse clouds that end in a 2-cycle between two pairing sets run to maxIterations in the
+    reference.  The device recognises the cycle (pose and pairing count repeating those of two iterations before,
+    twice in a row) and jumps to the end state: same iteration count, termination reason, pairing count and
+    quality as running the loop out (B200ICP_CYCLE=0 in a child process), poses within 1e-10 -- and equal to the
+    oracle's within the stated tolerance."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from mola_fe_lidar_b200 import scene
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    child = r"""
+import sys, json
+import numpy as np
+sys.path.insert(0, %r)
+from mola_fe_lidar_b200 import capi, scene
+icp = capi.ICP(capi.default_params())
+scans, _ = scene.make_sequence(13, seed=1)
+dec = [icp.voxel_decimate(icp.upload_raw(s), 1.0) for s in scans]
+out, guess = [], np.zeros(6)
+for i in range(1, 13):
+    r = icp.align(dec[i - 1], dec[i], guess)
+    out.append(dict(pose=[float(v).hex() for v in r["pose"]], cov=[float(v).hex() for v in r["cov"].ravel()],
+                    q=float(r["quality"]).hex(), it=int(r["n_iterations"]), term=int(r["termination_reason"]),
+                    npair=int(r["n_pairings"])))
+    guess = np.array([r["pose"][0], r["pose"][1], r["pose"][2], r["pose"][3], 0, 0])
+print(json.dumps(out))
+""" % root
+    runs = {}
+    for flag in ("2", "1", "0"):
+        env = dict(os.environ, B200ICP_CYCLE=flag)
+        p = subprocess.run([sys.executable, "-c", child], capture_output=True, text=True, env=env, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        runs[flag] = json.loads(p.stdout.strip().splitlines()[-1])
+    for a, b in zip(runs["2"], runs["0"]):
+        assert (a["it"], a["term"], a["npair"], a["q"]) == (b["it"], b["term"], b["npair"], b["q"])
+        pa = np.array([float.fromhex(v) for v in a["pose"]]), np.array([float.fromhex(v) for v in b["pose"]])
+        assert np.abs(pa[0] - pa[1]).max() < 1e-10
+        ca = np.array([float.fromhex(v) for v in a["cov"]]), np.array([float.fromhex(v) for v in b["cov"]])
+        assert np.allclose(ca[0], ca[1], rtol=1e-6, atol=1e-14)
+    assert runs["1"] == runs["0"]  # bitwise-only recognition never changes a bit
+    runs["1"] = runs["2"]
+    # the sequence must actually contain registrations that exhaust the iteration budget
+    assert any(r["term"] == 3 and r["it"] == 100 for r in runs["1"])
+    # and the oracle agrees on one of them
+    scans, _ = scene.make_sequence(13, seed=1)
+    k = next(i for i, r in enumerate(runs["1"]) if r["term"] == 3)
+    dec = [oracle.voxel_decimate(s, 1.0)[1] for s in scans[k:k + 2]]
+    prev = runs["1"][k - 1]["pose"] if k else None
+    guess = np.zeros(6) if k == 0 else np.array([float.fromhex(v) for v in prev[:4]] + [0.0, 0.0])
+    o = oracle.icp_align(oracle.Cloud(dec[0]), oracle.Cloud(dec[1]), guess, oracle.default_params(), kdtree=True)
+    g = runs["1"][k]
+    assert o["n_iterations"] == g["it"] and o["termination_reason"] == g["term"] and o["n_pairings"] == g["npair"]
+    pose = np.array([float.fromhex(v) for v in g["pose"]])
+    assert np.abs(pose[:3] - o["pose"][:3]).max() < TOL_T and np.abs(pose[3:] - o["pose"][3:]).max() < TOL_R

@@ -39,3 +39,42 @@ def test_voxel_edge_cases(icp, oracle, rng):
     # the decimated cloud is searchable
     idx, _ = icp.knn(out, out, 1, 0.7)
     assert np.array_equal(idx[:, 0], np.arange(len(out), dtype=np.uint32))
+
+
+def test_raw_upload_feeds_the_filter_only(icp, oracle, capi):
+    """apply_generators -> apply_filter_pipeline (LidarOdometry.cpp:215-224): the raw scan needs no search index
+    when a filter stage follows; its output is the same cloud, and a coordinates-only cloud is refused as a
+    side of a search."""
+    from mola_fe_lidar_b200 import scene
+    scans, _ = scene.make_sequence(1, seed=2)
+    raw = icp.upload_raw(scans[0])
+    out, keep = icp.voxel_decimate(raw, 1.0, want_indices=True)
+    okeep, oxyz = oracle.voxel_decimate(scans[0], 1.0)
+    assert np.array_equal(keep, okeep)
+    assert np.array_equal(out.download().view(np.uint32), oxyz.view(np.uint32))
+    with pytest.raises(capi.B200IcpError):
+        icp.knn(raw, out, 1, 0.7)
+    raw.free(), out.free()
+
+
+@pytest.mark.parametrize("res", [1.0, 0.5])
+def test_decimated_clouds_search_exact_with_coarse_cells(icp, oracle, res):
+    """A decimated cloud is indexed with cells that follow the voxel size (one point per voxel): neighbour lists
+    still equal the oracle's exact search, both as reference and as query side."""
+    from mola_fe_lidar_b200 import scene
+    scans, poses = scene.make_sequence(2, seed=3)
+    a = icp.voxel_decimate(icp.upload_raw(scans[0]), res)
+    b = icp.voxel_decimate(icp.upload_raw(scans[1]), res)
+    A, B = a.download(), b.download()
+    idx, d2 = icp.knn(a, b, 6, 0.7)
+    oidx, od2 = oracle.knn(oracle.Cloud(A), B, 6, 0.49, kdtree=True)
+    assert np.array_equal(idx, oidx)
+    assert np.array_equal(d2.view(np.uint32), od2.view(np.uint32))
+    # the decimated cloud against a raw (finely indexed) one and the other way round
+    raw = icp.upload(scans[0])
+    idx2, _ = icp.knn(raw, b, 6, 0.7)
+    oidx2, _ = oracle.knn(oracle.Cloud(scans[0]), B, 6, 0.49, kdtree=True)
+    assert np.array_equal(idx2, oidx2)
+    idx3, _ = icp.knn(a, raw, 1, 0.7)
+    oidx3, _ = oracle.knn(oracle.Cloud(A), scans[0], 1, 0.49, kdtree=True)
+    assert np.array_equal(idx3, oidx3)

@@ -74,6 +74,12 @@ void b200lo_wait_idle(b200lo_t* lo);
 int  b200lo_get_state(b200lo_t* lo, b200lo_state_t* out);
 /* factors the back-end received; returns the count (fills up to cap) */
 size_t b200lo_get_factors(b200lo_t* lo, b200lo_factor_t* out, size_t cap);
+/* The last loop-closure attempt (LidarOdometry.cpp:768-787): the Monte-Carlo guesses drawn (x y z yaw pitch
+ * roll each), the goodness each registration reached, the winner.  Returns the number of samples (fills up to
+ * cap); 0 when no loop closure has been attempted.  The reference draws from an unseeded generator (cpp:773);
+ * here the draws are reproducible (`b200_montecarlo_seed`) and reported, so that a harness can follow the branch. */
+size_t b200lo_last_montecarlo(b200lo_t* lo, uint64_t* from_kf, uint64_t* to_kf, double* guesses6, double* goodness,
+                              size_t cap, double* best_goodness, double* best_pose6);
 /* the scalar front-end parameters after YAML loading, as "key=value\n" text */
 size_t b200lo_dump_params(b200lo_t* lo, char* buf, size_t cap);
 /* profiler sections (name, count, total seconds, longest call) as "name,count,total,max\n" */

@@ -623,6 +623,16 @@ void LidarOdometry::doCheckForNonAdjacentKFs(ICP_Input::Ptr d)
                     icp_out.termination_reason = res[i].termination_reason;
                 }
             }
+            {
+                MonteCarloRecord rec;
+                rec.from_id = d->from_id, rec.to_id = d->to_id;
+                rec.guesses = guesses;
+                for (size_t i = 0; i < N; i++) rec.goodness.push_back(res[i].quality);
+                rec.best_goodness = icp_out.goodness;
+                b2::pose_to_ypr(icp_out.found_pose_to_wrt_from.mean, rec.best_pose);
+                std::lock_guard<std::mutex> lk(state_mtx_);
+                last_mc_ = std::move(rec);
+            }
             // d->init_guess_to_wrt_from keeps the LAST perturbed guess in the
             // reference (cpp:777-781 writes through d): same here
             if (N)

@@ -193,6 +193,23 @@ class LidarOdometry : public FrontEndBase
         return state_;
     }
 
+    /** The last loop-closure attempt (cpp:768-787), for harnesses: the guesses drawn, the goodness each one
+     *  reached and the winner.  The reference draws from an unseeded generator; a test can only follow the
+     *  branch when it is told what was drawn. */
+    struct MonteCarloRecord
+    {
+        id_t                from_id{INVALID_ID}, to_id{INVALID_ID};
+        std::vector<double> guesses;   // [n * 6] x y z yaw pitch roll
+        std::vector<double> goodness;  // [n]
+        double              best_goodness{0};
+        double              best_pose[6] = {0, 0, 0, 0, 0, 0};
+    };
+    MonteCarloRecord lastMonteCarlo() const
+    {
+        std::lock_guard<std::mutex> lk(state_mtx_);
+        return last_mc_;
+    }
+
     /** blocks until both worker pools are idle (harness helper) */
     void waitIdle();
     /** scans waiting in the 1-thread pool (what the drop rule of cpp:171-179 looks at) */
@@ -228,6 +245,7 @@ class LidarOdometry : public FrontEndBase
 
     std::mutex         local_pose_graph_mtx;
     mutable std::mutex state_mtx_;  // n_icp / n_dropped (touched by several threads) and stateCopy()
+    MonteCarloRecord   last_mc_;
     float              cloud_search_radius_{0.f};
     void               count_icp(size_t n)
     {

@@ -194,6 +194,24 @@ extern "C" int b200lo_get_state(b200lo_t* lo, b200lo_state_t* out)
     return 0;
 }
 
+extern "C" size_t b200lo_last_montecarlo(b200lo_t* lo, uint64_t* from_kf, uint64_t* to_kf, double* guesses6,
+                                         double* goodness, size_t cap, double* best_goodness, double* best_pose6)
+{
+    if (!lo) return 0;
+    const auto   r = lo->lo->lastMonteCarlo();
+    const size_t n = r.goodness.size();
+    if (from_kf) *from_kf = r.from_id;
+    if (to_kf) *to_kf = r.to_id;
+    for (size_t i = 0; i < n && i < cap; i++)
+    {
+        if (guesses6) memcpy(guesses6 + 6 * i, r.guesses.data() + 6 * i, 6 * sizeof(double));
+        if (goodness) goodness[i] = r.goodness[i];
+    }
+    if (best_goodness) *best_goodness = r.best_goodness;
+    if (best_pose6) memcpy(best_pose6, r.best_pose, sizeof(r.best_pose));
+    return n;
+}
+
 extern "C" size_t b200lo_get_factors(b200lo_t* lo, b200lo_factor_t* out, size_t cap)
 {
     if (!lo) return 0;

@@ -19,7 +19,7 @@ EXPORTS = [
     "b200lo_on_new_observation", "b200lo_enqueue_observation", "b200lo_queue_length",
     "b200lo_process_observation", "b200lo_spin_once",
     "b200lo_wait_idle", "b200lo_get_state", "b200lo_get_factors", "b200lo_dump_params",
-    "b200lo_dump_profile", "b200lo_icp_handle",
+    "b200lo_dump_profile", "b200lo_icp_handle", "b200lo_last_montecarlo",
 ]
 
 
@@ -78,6 +78,9 @@ def lib():
     L.b200lo_dump_params.restype = C.c_size_t
     L.b200lo_dump_profile.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.b200lo_dump_profile.restype = C.c_size_t
+    L.b200lo_last_montecarlo.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), vp, vp, C.c_size_t,
+                                         C.POINTER(C.c_double), vp]
+    L.b200lo_last_montecarlo.restype = C.c_size_t
     L.b200lo_icp_handle.argtypes = [vp, C.c_int]
     L.b200lo_icp_handle.restype = vp
     _lib = L
@@ -161,6 +164,19 @@ class LidarOdometry:
         arr = (Factor * max(n, 1))()
         n = lib().b200lo_get_factors(self.h, arr, n)
         return [(f.from_kf, f.to_kf, np.array(f.rel_pose)) for f in arr[:n]]
+
+    def last_montecarlo(self):
+        """The last loop-closure attempt: dict(from_kf, to_kf, guesses [n,6], goodness [n], best_goodness,
+        best_pose) or None."""
+        cap = 64
+        g, q, bp = np.zeros((cap, 6)), np.zeros(cap), np.zeros(6)
+        a, b, bg = C.c_uint64(), C.c_uint64(), C.c_double()
+        n = lib().b200lo_last_montecarlo(self.h, C.byref(a), C.byref(b), g.ctypes.data, q.ctypes.data, cap, C.byref(bg),
+                                         bp.ctypes.data)
+        if n == 0:
+            return None
+        return dict(from_kf=int(a.value), to_kf=int(b.value), guesses=g[:n].copy(), goodness=q[:n].copy(),
+                    best_goodness=float(bg.value), best_pose=bp)
 
     def _dump(self, fn):
         n = fn(self.h, None, 0)

@@ -191,3 +191,38 @@ print(json.dumps(out))
     assert o["n_iterations"] == g["it"] and o["termination_reason"] == g["term"] and o["n_pairings"] == g["npair"]
     pose = np.array([float.fromhex(v) for v in g["pose"]])
     assert np.abs(pose[:3] - o["pose"][:3]).max() < TOL_T and np.abs(pose[3:] - o["pose"][3:]).max() < TOL_R
+
+
+def test_concurrent_align_on_one_object(icp, oracle):
+    """One shared ICP object, align() called concurrently from the pool threads (LidarOdometry.h:167-172,
+    cpp:94-96, 711-729): eight threads register different pairs at once, several rounds; every result must be
+    the bits the same call gives alone, and agree with the oracle."""
+    import threading
+    from mola_fe_lidar_b200 import scene
+    pairs = []
+    for t in range(8):
+        A, B, _ = scene.make_pair_c1(seed=20 + t, n=4000 + 700 * t, sigma=0.005)
+        pairs.append((A, B, icp.upload(A), icp.upload(B)))
+    alone = [icp.align(p[2], p[3], np.zeros(6)) for p in pairs]
+    results, errors = [[None] * 4 for _ in range(8)], []
+
+    def work(t):
+        try:
+            for rep in range(4):
+                results[t][rep] = icp.align(pairs[t][2], pairs[t][3], np.zeros(6))
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errors, errors
+    for t in range(8):
+        for rep in range(4):
+            r = results[t][rep]
+            assert np.array_equal(r["pose"], alone[t]["pose"]) and np.array_equal(r["cov"], alone[t]["cov"])
+            for key in ("quality", "n_iterations", "termination_reason", "n_pairings"):
+                assert r[key] == alone[t][key]
+    o = oracle.icp_align(oracle.Cloud(pairs[3][0]), oracle.Cloud(pairs[3][1]), np.zeros(6), oracle.default_params(),
+                         kdtree=True)
+    _assert_same(alone[3], o)

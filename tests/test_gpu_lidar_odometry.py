@@ -132,11 +132,40 @@ def test_time_gate_label_filter_and_async_queue():
     lo.close()
 
 
+def _bfs_guess(edges, root, target, oracle):
+    """Pose of `target` wrt `root` along the breadth-first spanning tree the module builds over its local pose
+    graph (NetworkOfPoses3D::dijkstra_nodes_estimate: unit weights, neighbours in ascending id, first visit
+    wins; an edge (a, b) holds the pose of b wrt a and is inverted when walked from b)."""
+    adj = {}
+    for (a, b) in edges:
+        adj.setdefault(a, set()).add(b)
+        adj.setdefault(b, set()).add(a)
+    nodes, frontier = {root: np.zeros(6)}, [root]
+    while frontier:
+        nxt = []
+        for a in frontier:
+            for b in sorted(adj.get(a, ())):
+                if b in nodes:
+                    continue
+                if (a, b) in edges:
+                    rel = edges[(a, b)]
+                else:
+                    R, t = oracle.pose_to_Rt(edges[(b, a)])
+                    rel = oracle.Rt_to_pose(R.T, -R.T @ t)
+                nodes[b] = _compose(nodes[a], rel, oracle)
+                nxt.append(b)
+        frontier = nxt
+    return nodes[target]
+
+
 def test_extra_edges_between_nearby_keyframes(oracle, tmp_path):
     """checkForNearbyKFs + doCheckForNonAdjacentKFs (cpp:516-849): KFs >= 5 m apart get an extra factor.
     The synthetic 20k-point scans score a PairedRatio below the shipped 0.50 for
     key-frames that far apart, so the acceptance threshold (cpp:809-812) is
-    lowered in a copy of the parameter file; everything else is as shipped."""
+    lowered in a copy of the parameter file; everything else is as shipped.
+    Every extra factor is re-derived with the oracle: the key-frame clouds are the scans the reference flow
+    turns into key-frames, the initial guess is the spanning-tree pose over the factors present when the job
+    was made (cpp:674-675), and the registered pose must agree within the stated tolerance."""
     from mola_fe_lidar_b200 import lidar_odometry as lom, scene
     scans, poses = _sequence(14, n_pts=20000)
     txt = open(os.path.join(lom.PARAMS_DIR, "kitti-default.yaml")).read()
@@ -144,9 +173,12 @@ def test_extra_edges_between_nearby_keyframes(oracle, tmp_path):
     prm = tmp_path / "kitti-lowgood.yaml"
     prm.write_text(txt.replace("min_icp_goodness: 0.50", "min_icp_goodness: 0.05"))
     lo = lom.LidarOdometry(yaml_text=lom.system_yaml(params_file=str(prm)))
+    kf_scan = []  # scan index of every key-frame, in id order
     for i, s in enumerate(scans):
         lo.onNewObservation(s, 0.1 * i, sync=True)
-    lo.wait_idle()
+        lo.wait_idle()  # extra-edge jobs in a fixed order
+        while lo.state()["n_keyframes"] > len(kf_scan):
+            kf_scan.append(i)
     st = lo.state()
     f = lo.factors()
     assert st["n_keyframes"] >= 3 and st["n_checked_pairs"] >= 1
@@ -154,6 +186,69 @@ def test_extra_edges_between_nearby_keyframes(oracle, tmp_path):
     assert len(extra) >= 1, "expected at least one non-adjacent KF edge"
     assert st["n_factors"] == len(f) and st["n_localizations"] == 14
     lo.close()
+    # re-derive each extra factor with the oracle
+    prm_o = oracle.default_params()
+    clouds = {k: oracle.Cloud(scans[i]) for k, i in enumerate(kf_scan)}
+    # All extra-edge jobs of key-frame `a` are made together, right after its consecutive factor (a-1, a), from the
+    # graph as it is then; they complete on the pool threads in any order.  So: the graph is snapshotted when the
+    # consecutive factor of `a` is met, and every extra factor from `a` takes its guess from that snapshot.
+    edges, snapshot, checked = {}, {}, 0
+    for (a, b, pose) in f:
+        a, b = int(a), int(b)
+        if abs(b - a) > 1:
+            guess = _bfs_guess(snapshot[a], a, b, oracle)
+            o = oracle.icp_align(clouds[a], clouds[b], guess, prm_o, kdtree=True)
+            assert np.abs(pose[:3] - o["pose"][:3]).max() < TOL_T, (a, b, pose, o["pose"])
+            assert np.abs(pose[3:] - o["pose"][3:]).max() < TOL_R, (a, b, pose, o["pose"])
+            assert o["quality"] > 0.05
+            checked += 1
+        edges[(a, b)] = np.asarray(pose, dtype=np.float64)
+        if b - a == 1:
+            snapshot[b] = dict(edges)
+    assert checked == len(extra)
+
+
+def test_loop_closure_montecarlo_branch_matches_oracle(oracle, tmp_path):
+    """doCheckForNonAdjacentKFs, loop-closure branch (cpp:768-816): with the topological threshold lowered to 2
+    every non-adjacent key-frame in range is a loop-closure candidate, registered from
+    `loop_closure_montecarlo_samples` perturbed guesses (sigma 0.1 * max_dist_to_loop_closure in x, y, z and
+    2 deg in yaw, cpp:768-781) in ONE batched launch; the best goodness wins (cpp:785-786).  The module
+    reports the guesses it drew: the oracle registered from the same ten must pick the same winner."""
+    from mola_fe_lidar_b200 import lidar_odometry as lom
+    scans, poses = _sequence(9, n_pts=20000)
+    txt = open(os.path.join(lom.PARAMS_DIR, "kitti-default.yaml")).read()
+    txt = txt.replace("min_icp_goodness: 0.50", "min_icp_goodness: 0.05")
+    txt = txt.replace("min_icp_goodness_lc: 0.70", "min_icp_goodness_lc: 0.05")
+    assert "min_topo_dist_to_consider_loopclosure: 30" in txt
+    txt = txt.replace("min_topo_dist_to_consider_loopclosure: 30", "min_topo_dist_to_consider_loopclosure: 2")
+    prm = tmp_path / "kitti-lc.yaml"
+    prm.write_text(txt)
+    lo = lom.LidarOdometry(yaml_text=lom.system_yaml(params_file=str(prm), extra="  b200_montecarlo_seed: 7\n"))
+    kf_scan, seen = [], []
+    for i, s in enumerate(scans):
+        lo.onNewObservation(s, 0.1 * i, sync=True)
+        lo.wait_idle()
+        while lo.state()["n_keyframes"] > len(kf_scan):
+            kf_scan.append(i)
+        mc = lo.last_montecarlo()
+        if mc is not None and (not seen or (mc["from_kf"], mc["to_kf"]) != (seen[-1]["from_kf"], seen[-1]["to_kf"])):
+            seen.append(mc)
+    lo.close()
+    assert seen, "no loop-closure attempt was made"
+    prm_o = oracle.default_params()
+    for mc in seen:
+        assert mc["guesses"].shape == (10, 6) and len(mc["goodness"]) == 10
+        # the perturbation leaves pitch / roll alone (cpp:777-781)
+        assert np.all(mc["guesses"][:, 4:] == mc["guesses"][0, 4:])
+        a, b = oracle.Cloud(scans[kf_scan[mc["from_kf"]]]), oracle.Cloud(scans[kf_scan[mc["to_kf"]]])
+        res = [oracle.icp_align(a, b, g, prm_o, kdtree=True) for g in mc["guesses"]]
+        good = np.array([r["quality"] for r in res])
+        assert np.array_equal(good, mc["goodness"])
+        best = int(np.flatnonzero(good == good.max())[0])
+        if good.max() > 0:  # cpp:785: strictly better than the running best, so the FIRST maximum wins
+            assert np.abs(mc["best_pose"][:3] - res[best]["pose"][:3]).max() < TOL_T
+            assert np.abs(mc["best_pose"][3:] - res[best]["pose"][3:]).max() < TOL_R
+            assert mc["best_goodness"] == good.max()
 
 
 def test_keyframe_store_budget_gives_identical_factors(tmp_path):

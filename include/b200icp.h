@@ -262,6 +262,40 @@ int b200icp_knn_keys_exchange(b200icp_t* icp, const b200icp_cloud_t* ref, const 
 /* fills n keys at a device pointer with B200ICP_NO_KEY (exchange-buffer reset) */
 int b200icp_fill_no_key(b200icp_t* icp, uint64_t* d_keys, size_t n);
 
+/* --- a map sharded by spatial cell over the GPUs of one box, natively (NCCL owned by the library) ------------
+ * One process per GPU.  Rank 0 makes a communicator id and hands the 128 bytes to the others by any means (a
+ * file, MPI, a socket, torch.distributed); every rank then creates its communicator on its own b200icp_t.
+ * The reference holds one kd-tree per cloud in host memory and has no counterpart (BASELINE
+ * config 5): this is the `from` side of icp->align (LidarOdometry.cpp:869-871) when it is too large for one
+ * GPU's search. */
+#define B200ICP_COMM_ID_BYTES 128
+typedef struct b200icp_comm        b200icp_comm_t;
+typedef struct b200icp_sharded_map b200icp_sharded_map_t;
+int  b200icp_comm_unique_id(unsigned char id_out[B200ICP_COMM_ID_BYTES]);
+int  b200icp_comm_create(b200icp_t* icp, const unsigned char id[B200ICP_COMM_ID_BYTES], int world, int rank,
+                         b200icp_comm_t** out);
+void b200icp_comm_destroy(b200icp_comm_t* comm);
+/* Every rank passes the WHOLE map (host SoA).  The points are dealt to the ranks by coarse (x, y) cell of edge
+ * `cell` metres along a Morton curve -- round-robin (`interleaved`: every rank holds 1/world of every
+ * neighbourhood) or in `world` runs of equal point count -- the same partition on every rank.  A rank indexes
+ * its own cells and keeps a plain copy of all coordinates (16 B per point) for the plane fits. */
+int  b200icp_sharded_map_create(b200icp_comm_t* comm, const float* x, const float* y, const float* z, size_t n,
+                                float cell, int interleaved, float search_radius, b200icp_sharded_map_t** out);
+void b200icp_sharded_map_destroy(b200icp_sharded_map_t* map);
+size_t b200icp_sharded_map_local_size(const b200icp_sharded_map_t* map);
+/* b200icp_knn_keys_device against the whole map: every rank searches its shard, the partial lists are merged
+ * over NVLink (k = 1: ncclAllReduce(MIN) on the packed keys; k > 1: ncclAllGather + k-way merge kernel).  The same
+ * [nq*k] keys, GLOBAL indices, on every rank; collective: every rank calls it with the same queries. */
+int  b200icp_sharded_knn_keys(b200icp_sharded_map_t* map, const b200icp_cloud_t* queries, const double* pose6,
+                              uint32_t k, float max_dist, uint64_t* d_keys_out);
+/* b200icp_align_with against the whole map (collective: same local cloud, guess and call parameters on every
+ * rank).  Per outer iteration: search on every shard, the lists of a slice of the local points sent to the rank
+ * that owns the slice (reduce-scatter), k-way merge, plane fit and moments on the owner, one all-gather of the
+ * per-group moment partials, the same fixed-order sum and the same solve on every rank.  The result is
+ * BIT-IDENTICAL to b200icp_align against the unsharded map, on every rank.  Gauss-Newton solver only. */
+int  b200icp_sharded_align(b200icp_sharded_map_t* map, const b200icp_cloud_t* to_local, const double guess6[6],
+                           const b200icp_call_params_t* call, b200icp_result_t* out);
+
 /* --- matcher at a fixed pose (Matcher_Point2Plane; parity hook) ---------- */
 /* Host outputs in the local cloud's ORIGINAL order: paired[n] (0/1),
  * nn_idx[n*knn] (after the distance cut, padded INVALID), nn_cnt[n],

@@ -113,6 +113,9 @@ EXPORTS = [
     "b200icp_match", "b200icp_align", "b200icp_align_with", "b200icp_call_params_of",
     "b200icp_align_batch", "b200icp_profile_enable", "b200icp_profile_reset",
     "b200icp_profile_get", "b200icp_synchronize",
+    "b200icp_comm_unique_id", "b200icp_comm_create", "b200icp_comm_destroy", "b200icp_sharded_map_create",
+    "b200icp_sharded_map_destroy", "b200icp_sharded_map_local_size", "b200icp_sharded_knn_keys",
+    "b200icp_sharded_align",
 ]
 
 _lib = None
@@ -168,6 +171,17 @@ def lib():
     L.b200icp_align_with.argtypes = [vp, vp, vp, dp, C.POINTER(CallParams), C.POINTER(Result)]
     L.b200icp_call_params_of.argtypes = [C.POINTER(Params), C.POINTER(CallParams)]
     L.b200icp_call_params_of.restype = None
+    L.b200icp_comm_unique_id.argtypes = [C.c_char_p]
+    L.b200icp_comm_create.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
+    L.b200icp_comm_destroy.argtypes = [vp]
+    L.b200icp_comm_destroy.restype = None
+    L.b200icp_sharded_map_create.argtypes = [vp, vp, vp, vp, C.c_size_t, C.c_float, C.c_int, C.c_float, C.POINTER(vp)]
+    L.b200icp_sharded_map_destroy.argtypes = [vp]
+    L.b200icp_sharded_map_destroy.restype = None
+    L.b200icp_sharded_map_local_size.argtypes = [vp]
+    L.b200icp_sharded_map_local_size.restype = C.c_size_t
+    L.b200icp_sharded_knn_keys.argtypes = [vp, vp, dp, C.c_uint32, C.c_float, vp]
+    L.b200icp_sharded_align.argtypes = [vp, vp, dp, C.POINTER(CallParams), C.POINTER(Result)]
     L.b200icp_align_batch.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(vp), dp,
                                       C.POINTER(Result)]
     L.b200icp_profile_enable.argtypes = [vp, C.c_int]
@@ -462,3 +476,58 @@ class ICP:
 
 def device_count():
     return lib().b200icp_device_count()
+
+
+# ---- a map sharded over the GPUs of one box, natively (the library owns the NCCL communicator) --------------
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """128 bytes for b200icp_comm_create; made by ONE rank and handed to the others by any means."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    _check(lib().b200icp_comm_unique_id(buf))
+    return buf.raw
+
+
+class Comm:
+    def __init__(self, icp, unique_id, world, rank):
+        self.icp, self.world, self.rank = icp, world, rank
+        h = C.c_void_p()
+        _check(lib().b200icp_comm_create(icp.h, unique_id, world, rank, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            lib().b200icp_comm_destroy(self.h)
+            self.h = None
+
+
+class NativeShardedMap:
+    """b200icp_sharded_map_*: every rank passes the whole map, keeps the cells it owns."""
+
+    def __init__(self, comm, xyz, cell=4.0, interleaved=True, search_radius=0.0):
+        self.comm = comm
+        xyz = np.asarray(xyz, dtype=np.float32).reshape(-1, 3)
+        x, y, z = (np.ascontiguousarray(xyz[:, i]) for i in range(3))
+        h = C.c_void_p()
+        _check(lib().b200icp_sharded_map_create(comm.h, x.ctypes.data, y.ctypes.data, z.ctypes.data, len(x), cell,
+                                                int(interleaved), search_radius, C.byref(h)))
+        self.h = h
+
+    def local_size(self):
+        return int(lib().b200icp_sharded_map_local_size(self.h))
+
+    def knn_keys(self, queries, k, max_dist, d_keys_ptr, pose6=None):
+        p = None if pose6 is None else _ptr(np.ascontiguousarray(pose6, dtype=np.float64), C.c_double)
+        _check(lib().b200icp_sharded_knn_keys(self.h, queries.h, p, k, max_dist, d_keys_ptr))
+
+    def align(self, to_local, guess6=None):
+        g = np.ascontiguousarray(np.zeros(6) if guess6 is None else guess6, dtype=np.float64)
+        r = Result()
+        _check(lib().b200icp_sharded_align(self.h, to_local.h, _ptr(g, C.c_double), None, C.byref(r)))
+        return r.as_dict()
+
+    def close(self):
+        if self.h:
+            lib().b200icp_sharded_map_destroy(self.h)
+            self.h = None

@@ -30,6 +30,9 @@
 #include "sweep_search.cuh"
 #include "runtime.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <cfloat>
 #include <cstdlib>
@@ -146,14 +149,16 @@ struct NnWriter
 // renumbers shard-local indices to the caller's global ones
 struct KeyWriter
 {
-    uint64_t*       keys;  // [rows * k], row = original index of the query
-    const uint32_t* map;   // or null
+    uint64_t*       keys;    // [rows * k], row = original index of the query (by_pos: its sorted position)
+    const uint32_t* map;     // or null
     uint32_t        k;
+    uint32_t        by_pos;  // sharded registration: rows in the local cloud's sorted order, as the fit stage reads them
     template <int K>
-    __device__ __forceinline__ void operator()(JobDev&, const CloudView&, bool has, uint32_t, uint32_t orig,
+    __device__ __forceinline__ void operator()(JobDev&, const CloudView&, bool has, uint32_t pos, uint32_t orig,
                                                const uint64_t (&key)[K], uint64_t sent) const
     {
         if (!has) return;
+        if (by_pos) orig = pos;
 #pragma unroll
         for (int i = 0; i < K; i++)
             if ((uint32_t)i < k)
@@ -599,7 +604,7 @@ __device__ __forceinline__ void sum_records(const double* base, uint32_t count, 
 // reduced moments: in sS[192] (shared) and in J.M.
 __device__ __forceinline__ bool deliver_chunk(JobDev& J, uint32_t chunk, uint32_t n_chunks, const double (&c00)[2],
                                               const double (&c01)[2], const double (&c11)[2],
-                                              const FitBuffers& fb, double* sS)
+                                              const FitBuffers& fb, double* sS, bool groups_only)
 {
     const int lane = threadIdx.x & 31;
     int       idx[6];
@@ -623,6 +628,7 @@ __device__ __forceinline__ bool deliver_chunk(JobDev& J, uint32_t chunk, uint32_
 #pragma unroll
     for (int i = 0; i < 6; i++) gp[idx[i]] = v[i];
     if (lane == 0) fb.tickets[J.group_base + g] = 0;  // ready for the next launch
+    if (groups_only) return false;  // sharded registration: the group partials of all ranks are summed after the exchange
     __threadfence();
     __syncwarp();
     if (lane == 0) t = atomicAdd(&J.groups_done, 1u);
@@ -678,7 +684,8 @@ template <int K, bool WRITE>
 __global__ void __launch_bounds__(kChunk, 4)
     fit_plane_kernel(const CloudView* __restrict__ clouds, JobDev* __restrict__ jobs,
                      const uint32_t* __restrict__ nn, FitBuffers fb, uint32_t chunk_items, int tail_mode,
-                     IcpDevParams P, MatchOut out, PairRec* __restrict__ pairs, uint32_t* __restrict__ n_active)
+                     IcpDevParams P, MatchOut out, PairRec* __restrict__ pairs, uint32_t* __restrict__ n_active,
+                     uint32_t chunk_begin, uint32_t chunk_end)
 {
     const uint32_t job = blockIdx.y;
     JobDev&        J = jobs[job];
@@ -698,14 +705,15 @@ __global__ void __launch_bounds__(kChunk, 4)
     double*        st = sm.stage[warp];
     if (n_chunks == 0)
     {
-        if (blockIdx.x == 0 && warp == 0) fit_job_without_chunks(J, sm, tail_mode, P, n_active);
+        if (blockIdx.x == 0 && warp == 0 && tail_mode != 2) fit_job_without_chunks(J, sm, tail_mode, P, n_active);
         return;
     }
 
     // the delivery that completes a job is always some warp's LAST chunk: the tail runs after the loop, when
-    // nothing of the loop is live any more
+    // nothing of the loop is live any more.  [chunk_begin, chunk_end): the chunks this launch is responsible for
+    // (all of them, or this rank's slice of a sharded registration -- tail_mode 2: group partials only)
     bool completes_job = false;
-    for (uint32_t chunk = item_warp_id(); chunk < n_chunks; chunk += item_warp_count())
+    for (uint32_t chunk = chunk_begin + item_warp_id(); chunk < min(n_chunks, chunk_end); chunk += item_warp_count())
     {
       double c00[2] = {0, 0}, c01[2] = {0, 0}, c11[2] = {0, 0};
       for (uint32_t item = chunk * chunk_items; item < min(n_items, (chunk + 1) * chunk_items); item++)
@@ -830,7 +838,7 @@ __global__ void __launch_bounds__(kChunk, 4)
         e[12] = r0, e[13] = f1, e[14] = 0.0, e[15] = 0.0;
         accumulate_moments(st, paired, e, c00, c01, c11);
       }
-      completes_job = deliver_chunk(J, chunk, n_chunks, c00, c01, c11, fb, sm.solve.S);
+      completes_job = deliver_chunk(J, chunk, n_chunks, c00, c01, c11, fb, sm.solve.S, tail_mode == 2);
     }
     if (completes_job) fit_job_tail(J, sm, tail_mode, P, n_active);
 }
@@ -845,7 +853,8 @@ template <bool WRITE>
 __global__ void __launch_bounds__(kChunk)
     fit_p2p_kernel(const CloudView* __restrict__ clouds, JobDev* __restrict__ jobs,
                    const uint32_t* __restrict__ nn, FitBuffers fb, uint32_t chunk_items, int tail_mode,
-                   IcpDevParams P, MatchOut out, PairRec* __restrict__ pairs, uint32_t* __restrict__ n_active)
+                   IcpDevParams P, MatchOut out, PairRec* __restrict__ pairs, uint32_t* __restrict__ n_active,
+                   uint32_t chunk_begin, uint32_t chunk_end)
 {
     const uint32_t job = blockIdx.y;
     JobDev&        J = jobs[job];
@@ -865,14 +874,15 @@ __global__ void __launch_bounds__(kChunk)
     double*        st = sm.stage[warp];
     if (n_chunks == 0)
     {
-        if (blockIdx.x == 0 && warp == 0) fit_job_without_chunks(J, sm, tail_mode, P, n_active);
+        if (blockIdx.x == 0 && warp == 0 && tail_mode != 2) fit_job_without_chunks(J, sm, tail_mode, P, n_active);
         return;
     }
 
     // the delivery that completes a job is always some warp's LAST chunk: the tail runs after the loop, when
-    // nothing of the loop is live any more
+    // nothing of the loop is live any more.  [chunk_begin, chunk_end): the chunks this launch is responsible for
+    // (all of them, or this rank's slice of a sharded registration -- tail_mode 2: group partials only)
     bool completes_job = false;
-    for (uint32_t chunk = item_warp_id(); chunk < n_chunks; chunk += item_warp_count())
+    for (uint32_t chunk = chunk_begin + item_warp_id(); chunk < min(n_chunks, chunk_end); chunk += item_warp_count())
     {
       double c00[2] = {0, 0}, c01[2] = {0, 0}, c11[2] = {0, 0};
       for (uint32_t item = chunk * chunk_items; item < min(n_items, (chunk + 1) * chunk_items); item++)
@@ -924,7 +934,7 @@ __global__ void __launch_bounds__(kChunk)
         for (int i = 7; i < 16; i++) e[i] = 0.0;
         accumulate_moments(st, paired, e, c00, c01, c11);
       }
-      completes_job = deliver_chunk(J, chunk, n_chunks, c00, c01, c11, fb, sm.solve.S);
+      completes_job = deliver_chunk(J, chunk, n_chunks, c00, c01, c11, fb, sm.solve.S, tail_mode == 2);
     }
     if (completes_job) fit_job_tail(J, sm, tail_mode, P, n_active);
 }
@@ -1565,22 +1575,23 @@ static void launch_match_search(const ::b200icp* ctx, Workspace* ws, const IcpDe
 template <bool WRITE>
 static void launch_fit(Workspace* ws, const IcpDevParams& D, dim3 grid, const CloudView* d_clouds, JobDev* d_jobs,
                        const uint32_t* d_nn, const FitBuffers& fb, uint32_t chunk_items, int tail_mode,
-                       const MatchOut& mo, PairRec* d_pairs, uint32_t* d_active)
+                       const MatchOut& mo, PairRec* d_pairs, uint32_t* d_active, uint32_t chunk_begin = 0,
+                       uint32_t chunk_end = 0xFFFFFFFFu)
 {
     cudaStream_t s = ws->stream;
     const int    K = matcher_k(D);
     if (K == 1)
         fit_p2p_kernel<WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_nn, fb, chunk_items, tail_mode, D, mo, d_pairs,
-                                                      d_active);
+                                                      d_active, chunk_begin, chunk_end);
     else if (K == 4)
         fit_plane_kernel<4, WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_nn, fb, chunk_items, tail_mode, D, mo,
-                                                           d_pairs, d_active);
+                                                           d_pairs, d_active, chunk_begin, chunk_end);
     else if (K == 6)
         fit_plane_kernel<6, WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_nn, fb, chunk_items, tail_mode, D, mo,
-                                                           d_pairs, d_active);
+                                                           d_pairs, d_active, chunk_begin, chunk_end);
     else
         fit_plane_kernel<8, WRITE><<<grid, kChunk, 0, s>>>(d_clouds, d_jobs, d_nn, fb, chunk_items, tail_mode, D, mo,
-                                                           d_pairs, d_active);
+                                                           d_pairs, d_active, chunk_begin, chunk_end);
     ws->launches++;
 }
 
@@ -2568,5 +2579,7 @@ int run_match(::b200icp* ctx, const b200icp_cloud* from, const b200icp_cloud* to
         *n_pairings = (uint32_t)(pairing_count(hj->M, D.matcher_kind == B200ICP_MATCHER_POINTS_DISTANCE) + 0.5);
     return B200ICP_OK;
 }
+
+#include "sharded.inl"
 
 }  // namespace b2

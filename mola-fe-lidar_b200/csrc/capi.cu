@@ -475,6 +475,63 @@ extern "C" int b200icp_align_batch(b200icp_t* icp, size_t n, const b200icp_cloud
     return run_align_batch(icp, n, from_global, to_local, guesses6, nullptr, out);
 }
 
+// ---- sharded maps (sharded.inl) ---------------------------------------------------------------------------
+extern "C" int b200icp_comm_unique_id(unsigned char id_out[B200ICP_COMM_ID_BYTES])
+{
+    if (!id_out)
+    {
+        set_error("null argument");
+        return B200ICP_ERR_BAD_ARG;
+    }
+    return run_comm_unique_id(id_out);
+}
+extern "C" int b200icp_comm_create(b200icp_t* icp, const unsigned char id[B200ICP_COMM_ID_BYTES], int world, int rank,
+                                   b200icp_comm_t** out)
+{
+    if (!icp || !id || !out || world < 1 || rank < 0 || rank >= world)
+    {
+        set_error("null argument or rank outside [0, world)");
+        return B200ICP_ERR_BAD_ARG;
+    }
+    *out = nullptr;
+    return run_comm_create(icp, id, world, rank, out);
+}
+extern "C" void b200icp_comm_destroy(b200icp_comm_t* comm) { run_comm_destroy(comm); }
+extern "C" int b200icp_sharded_map_create(b200icp_comm_t* comm, const float* x, const float* y, const float* z, size_t n,
+                                          float cell, int interleaved, float search_radius,
+                                          b200icp_sharded_map_t** out)
+{
+    if (!comm || !out || (n && (!x || !y || !z)))
+    {
+        set_error("null argument");
+        return B200ICP_ERR_BAD_ARG;
+    }
+    *out = nullptr;
+    return run_sharded_map_create(comm, x, y, z, n, cell, interleaved, search_radius, out);
+}
+extern "C" void   b200icp_sharded_map_destroy(b200icp_sharded_map_t* map) { run_sharded_map_destroy(map); }
+extern "C" size_t b200icp_sharded_map_local_size(const b200icp_sharded_map_t* map) { return run_sharded_map_local_size(map); }
+extern "C" int b200icp_sharded_knn_keys(b200icp_sharded_map_t* map, const b200icp_cloud_t* queries, const double* pose6,
+                                        uint32_t k, float max_dist, uint64_t* d_keys_out)
+{
+    if (!map || !queries || !d_keys_out)
+    {
+        set_error("null argument");
+        return B200ICP_ERR_BAD_ARG;
+    }
+    return run_sharded_knn_keys(map, queries, pose6, k, max_dist, d_keys_out);
+}
+extern "C" int b200icp_sharded_align(b200icp_sharded_map_t* map, const b200icp_cloud_t* to_local, const double guess6[6],
+                                     const b200icp_call_params_t* call, b200icp_result_t* out)
+{
+    if (!map || !to_local || !guess6 || !out)
+    {
+        set_error("null argument");
+        return B200ICP_ERR_BAD_ARG;
+    }
+    return run_sharded_align(map, to_local, guess6, call, out);
+}
+
 extern "C" void b200icp_profile_enable(b200icp_t* icp, int enable)
 {
     if (icp) icp->profile_on = enable != 0;

@@ -241,5 +241,18 @@ int run_match(::b200icp* ctx, const b200icp_cloud* from, const b200icp_cloud* to
 int run_voxel(::b200icp* ctx, const b200icp_cloud* in, float resolution, int use_average,
               float search_radius, b200icp_cloud** out, uint32_t* keep_idx);
 
+// sharded maps over the GPUs of one box (sharded.inl); the library owns the NCCL communicator
+int  run_comm_unique_id(unsigned char* id_out);
+int  run_comm_create(::b200icp* ctx, const unsigned char* id_bytes, int world, int rank, b200icp_comm** out);
+void run_comm_destroy(b200icp_comm* c);
+int  run_sharded_map_create(b200icp_comm* comm, const float* x, const float* y, const float* z, size_t n, float cell,
+                            int interleaved, float search_radius, b200icp_sharded_map** out);
+void run_sharded_map_destroy(b200icp_sharded_map* m);
+size_t run_sharded_map_local_size(const b200icp_sharded_map* m);
+int  run_sharded_knn_keys(b200icp_sharded_map* m, const b200icp_cloud* q, const double* pose6, uint32_t k,
+                          float max_dist, uint64_t* d_keys_out);
+int  run_sharded_align(b200icp_sharded_map* m, const b200icp_cloud* to, const double* guess6,
+                       const b200icp_call_params_t* call, b200icp_result_t* out);
+
 void make_dev_params(const b200icp_params_t& P, IcpDevParams& D);
 }  // namespace b2

@@ -472,6 +472,91 @@ def sharded_knn(torch, dist, capi, scans, poses, rank, world, local_rank, dev, m
     return out
 
 
+def sharded_native(torch, dist, capi, scans, poses, rank, world, local_rank, dev, map_per_gpu):
+    """Config C5 through the library's own multi-GPU host (b200icp_comm_* / b200icp_sharded_*, csrc/sharded.inl):
+    the NCCL communicator is the library's, nothing of torch.distributed is in the data path (it only hands the
+    communicator id around).  kNN against the sharded map, and a whole REGISTRATION of the 128-beam scan against
+    it -- bit-identical to the unsharded registration, which rank 0 also runs (the whole map fits one B200) and
+    compares."""
+    from mola_fe_lidar_b200 import scene
+    icp = capi.ICP(capi.default_params(), device=local_rank)
+    ids = [capi.comm_unique_id() if rank == 0 else None]
+    if dist is not None:
+        dist.broadcast_object_list(ids, src=0)
+    comm = capi.Comm(icp, ids[0], world, rank)
+    wp = np.concatenate(world_points(scans, poses))
+    rng = np.random.default_rng(5)  # the same map on every rank (as in sharded_knn)
+    ctr = wp.mean(axis=0)
+    near = wp[(np.abs(wp[:, 0] - ctr[0]) < 60.0) & (np.abs(wp[:, 1] - ctr[1]) < 60.0)]
+    reps = (map_per_gpu + len(near) - 1) // len(near)
+    stretch = np.concatenate([near + rng.normal(0, 0.03, size=near.shape).astype(np.float32)
+                              for _ in range(reps)])[:map_per_gpu]
+    themap = np.concatenate([stretch + np.float32([130.0 * (j % 3), 130.0 * (j // 3), 0.0]) for j in range(world)])
+    q_pose = scene.trajectory(6)[5]
+    q_scan = scene.make_scan(scene.World(1), q_pose, np.random.default_rng(1005), n_beams=128, n_azimuth=2032,
+                             elev=(15.0, -25.0))
+    truth = scene.matrix_to_pose6(q_pose)
+    guess = truth + np.array([0.10, -0.05, 0.02, 0.003, 0.0, 0.0])
+    smap = capi.NativeShardedMap(comm, themap, cell=4.0, interleaved=True, search_radius=0.7)
+    local = icp.upload(q_scan)
+    out = {"workload": "c5_sharded_map_native", "map_points": int(len(themap)), "map_points_this_rank": smap.local_size(),
+           "scan_points": int(len(q_scan)), "host": "C++ (libb200icp.so owns the NCCL communicator)", "knn": []}
+
+    def maxed(ms):
+        if dist is None:
+            return ms
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt[0])
+
+    keep = {}
+    for k in (1, 6):
+        keys = torch.empty((len(q_scan), k), dtype=torch.int64, device=dev)
+        smap.knn_keys(local, k, 0.7, keys.data_ptr(), pose6=truth)
+        ms = 1e30
+        for _ in range(4):
+            m1, _ = timed(torch, lambda: smap.knn_keys(local, k, 0.7, keys.data_ptr(), pose6=truth))
+            ms = min(ms, maxed(m1))
+        keep[k] = keys
+        out["knn"].append({"k": k, "ms": ms, "queries_per_s": len(q_scan) / (ms * 1e-3),
+                           "merge": "ncclAllReduce(MIN, uint64)" if k == 1 else "ncclAllGather + k-way merge kernel"})
+    r = smap.align(local, guess)  # warm-up
+    ms = 1e30
+    for _ in range(3):
+        m1, r = timed(torch, lambda: smap.align(local, guess))
+        ms = min(ms, maxed(m1))
+    out["registration"] = {"ms": ms, "registrations_per_s": 1e3 / ms, "outer_iterations": int(r["n_iterations"]) + 1,
+                           "quality": float(r["quality"]), "n_pairings": int(r["n_pairings"]),
+                           "max_abs_translation_error_m": float(np.abs(r["pose"][:3] - truth[:3]).max()),
+                           "per_iteration": "search on every shard, reduce-scatter of the lists by slice "
+                                            "(ncclSend/ncclRecv), k-way merge + plane fit + moments on the owner, "
+                                            "all-gather of the group partials, the same solve on every rank"}
+    if rank == 0:  # the unsharded map on ONE GPU: same keys, same registration, bit for bit
+        try:
+            whole = icp.upload(themap, search_radius=0.7)
+            same_keys = {}
+            for k in (1, 6):
+                kp = torch.empty((len(q_scan), k), dtype=torch.int64, device=dev)
+                icp.knn_keys_device(whole, local, k, 0.7, kp.data_ptr(), pose6=truth)
+                torch.cuda.synchronize()
+                same_keys[k] = bool(torch.equal(kp, keep[k]))
+            ms1, r1 = timed(torch, lambda: icp.align(whole, local, guess))
+            out["unsharded_on_one_gpu"] = {
+                "keys_identical": same_keys, "registration_ms": ms1,
+                "registration_identical": bool(np.array_equal(r1["pose"], r["pose"]) and np.array_equal(r1["cov"], r["cov"])
+                                               and r1["n_iterations"] == r["n_iterations"] and r1["quality"] == r["quality"])}
+            whole.free()
+        except Exception as e:
+            out["unsharded_on_one_gpu"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    if dist is not None:
+        dist.barrier()
+    local.free()
+    smap.close()
+    comm.close()
+    icp.close()
+    return out
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     from mola_fe_lidar_b200 import capi, lidar_odometry
@@ -660,6 +745,10 @@ def run_b200(args, rank, world, local_rank):
                                                        local_rank, dev, args.map_points_per_gpu))
         if r is not None:
             extras["sharded_knn"] = r
+        r = section("sharded_native", lambda: sharded_native(torch, dist, capi, shared_scans, shared_poses, rank, world,
+                                                             local_rank, dev, args.map_points_per_gpu))
+        if r is not None:
+            extras["sharded_native"] = r
 
     if rank == 0:
         launches = max(prof["match_launches"], 1)

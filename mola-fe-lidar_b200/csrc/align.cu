@@ -380,26 +380,26 @@ __device__ __forceinline__ float seeded_cap(const CloudView& cvG, const uint32_t
     return fminf(cap_d2, worst);
 }
 
-// Warps draw items from the job's counter (dynamic: the results do not depend
-// on who searches what, and items differ a lot in cost); the next item is drawn
-// while the current one is searched.  Per item (<= 32 queries, one per lane; items
-// are plain runs of kItem sorted points, cloud.cu): caps -> box of the queries'
-// home cells -> tile -> item sweep (item_sweep.cuh) -> shell walk for the lanes the
-// sweep left out.  A group of lanes whose tile does not fit (queries spread over
-// far-apart blocks) is split in two, down to single lanes, which take the hash
-// walk of knn_search.cuh.
+// ---- the item sweep (item_sweep.cuh) as the search stage ---------------------
+// Warps draw items from the job's counter (dynamic: the results do not depend on
+// who searches what, and items differ in cost); the next item is drawn while the
+// current one is searched.  Items are plain runs of kItem sorted points of the
+// local cloud (cloud.cu).  A group of lanes too far apart for one box (a run
+// that straddles a jump of the Morton curve) is split in two, down to single
+// lanes, which search alone.
 template <int K, class F>
-__device__ __forceinline__ void for_each_item(WarpTile& W, SweepSmem& SW, const CloudView& cvL, const CloudView& cvG,
-                                              const GridDev& grid, const double* Rt, uint32_t n_items,
-                                              uint32_t n_local, uint32_t* next_item, float cap_d2, bool sweep_on,
-                                              const SeedRows& seed, F&& f)
+__device__ __forceinline__ void for_each_item_sweep(SweepSmem& SW, const CloudView& cvL, const CloudView& cvG,
+                                                    const GridDev& grid, const double* Rt, uint32_t n_items,
+                                                    uint32_t n_local, uint32_t* next_item, float cap_d2,
+                                                    bool bulk, const SeedRows& seed, F&& f)
 {
     const int      lane = threadIdx.x & 31;
     const unsigned full = 0xFFFFFFFFu;
-    const int      Smax = search_shells(grid, cap_d2);
+    uint32_t       par = 0;  // phase parities of the warp's two stage mbarriers (bulk-copy variant)
     uint32_t       item = 0;
     if (lane == 0) item = atomicAdd(next_item, 1u);
     item = __shfl_sync(full, item, 0);
+#pragma unroll 1
     while (item < n_items)
     {
         uint32_t nxt = 0;
@@ -414,72 +414,159 @@ __device__ __forceinline__ void for_each_item(WarpTile& W, SweepSmem& SW, const 
         double gx, gy, gz;
         transform_point(Rt, pl, gx, gy, gz);
         const float qx = (float)gx, qy = (float)gy, qz = (float)gz;
-        const bool  finite = has && (fabsf(qx) <= FLT_MAX) && (fabsf(qy) <= FLT_MAX) && (fabsf(qz) <= FLT_MAX);
+        // a query with a NaN / infinite coordinate has no neighbours
+        const bool  hasq = has && (fabsf(qx) <= FLT_MAX) && (fabsf(qy) <= FLT_MAX) && (fabsf(qz) <= FLT_MAX);
         // this lane's radius cap: the caller's, or the tighter bound of its seeds
         float cap = cap_d2;
-        if (seed.rows && finite)
+        if (seed.rows && hasq)
             cap = seeded_cap<K>(cvG, seed.rows + (size_t)(first + lane) * seed.k, seed.k, qx, qy, qz, cap_d2);
-        const QueryCell qc = locate_query(grid, Smax, qx, qy, qz);
-        const bool      hasq = has && qc.valid;
-        uint64_t        sent = sentinel_key(cap);
-        uint64_t        key[K];
+        uint64_t sent = sentinel_key(cap);
+        uint64_t key[K];
 #pragma unroll
         for (int i = 0; i < K; i++) key[i] = sent;
         B2_PHASE(0);
-        bool     any_tiled = false;
         uint32_t stack[6];
         int      sp = 0;
         stack[sp++] = __ballot_sync(full, hasq);
+#pragma unroll 1
         while (sp > 0)
         {
             const uint32_t mask = stack[--sp];
             if (mask == 0u) continue;
             const bool in = (mask >> lane) & 1u;
-            // shells the widest lane of the group may need (warp-uniform); unseeded: the radius cap
-            const float capmax = __uint_as_float(__reduce_max_sync(full, in ? __float_as_uint(cap) : 0u));
-            const int   S = search_shells(grid, capmax);
-            int         lo[3] = {in ? qc.hx : INT_MAX, in ? qc.hy : INT_MAX, in ? qc.hz : INT_MAX};
-            int         hi[3] = {in ? qc.hx : INT_MIN, in ? qc.hy : INT_MIN, in ? qc.hz : INT_MIN};
-#pragma unroll
-            for (int d = 0; d < 3; d++)
-            {
-                lo[d] = __reduce_min_sync(full, lo[d]);
-                hi[d] = __reduce_max_sync(full, hi[d]);
-            }
-            TileGeom   G;
-            const bool tiled = warp_tile_build(W, G, cvG, lo, hi, S);
-            B2_PHASE(1);
             B2_COUNT(12, 1);
-            if (!tiled)
+            if (item_sweep<K>(cvG, grid, SW, in, seed.rows != nullptr, bulk, par, qx, qy, qz, cap, key, sent) == 0) continue;
+            const int n = __popc(mask);
+            if (n == 1)
             {
-                const int n = __popc(mask);
-                if (n == 1)
-                {
-                    if (in) knn_search<K>(cvG, grid, qx, qy, qz, cap, key);
-                    continue;
-                }
-                // lower half of the group's lanes first
-                const uint32_t cut = __fns(mask, 0u, n / 2 + 1);
-                const uint32_t lower = mask & ((1u << cut) - 1u);
-                stack[sp++] = mask & ~lower;
-                stack[sp++] = lower;
+                if (in) knn_search<K>(cvG, grid, qx, qy, qz, cap, key);
                 continue;
             }
-            any_tiled = true;
-            bool done = false;
-            if (sweep_on) done = item_sweep<K>(W, G, cvG, grid, SW, S, in, seed.rows == nullptr, qx, qy, qz, cap, key, sent);
-#ifdef B200ICP_DBG_PHASES
-            b2_ph_t = clock64();
-#endif
-            if (in && !done) tile_knn<K>(W, G, cvG, grid, qc, S, qx, qy, qz, key);
-            __syncwarp();
-            B2_PHASE(5);
+            // lanes too far apart for one box: lower half first
+            const uint32_t cut = __fns(mask, 0u, n / 2 + 1);
+            const uint32_t lower = mask & ((1u << cut) - 1u);
+            stack[sp++] = mask & ~lower;
+            stack[sp++] = lower;
         }
+#ifdef B200ICP_DBG_PHASES
+        b2_ph_t = clock64();
+#endif
         f(has, first + lane, __float_as_uint(pl.w), key, sent);
         B2_PHASE(6);
         if (g_dbg_item_cycles && lane == 0)
-            g_dbg_item_cycles[item] =
-                (uint32_t)min((long long)0x7FFFFFFF, clock64() - dbg_t0) | (any_tiled ? 0u : 0x80000000u);
+            g_dbg_item_cycles[item] = (uint32_t)min((long long)0x7FFFFFFF, clock64() - dbg_t0);
+        item = __shfl_sync(full, nxt, 0);
+    }
+}
+
+struct ItemSmem
+{
+    SweepSmem sweep[kChunk / 32];
+    GridDev   grid;
+    double    Rt[12];
+    uint32_t  n_items, n_local;
+};
+
+// The search stage.  seed_nn / seed_k: the launch's neighbour-row buffer of an
+// earlier matcher search (rows of job j start at J.pair_base); used when the
+// job says its rows are valid (JobDev::rows_valid, set by the solver after a
+// matcher run).  Dynamic shared memory: sizeof(ItemSmem) (launch_search_k opts in).
+#ifndef B200ICP_ITEM_MINB
+#define B200ICP_ITEM_MINB 4
+#endif
+template <int K, class Epi>
+__global__ void __launch_bounds__(kChunk, B200ICP_ITEM_MINB)
+    search_item_kernel(const CloudView* __restrict__ clouds, JobDev* __restrict__ jobs, IcpDevParams P,
+                       float cap_d2, int gate, const uint32_t* seed_nn, uint32_t seed_k, int bulk, Epi epi)
+{
+    JobDev& J = jobs[blockIdx.y];
+    if (gate == 1 && (J.status != 0 || !matcher_active(P, J.iter))) return;  // matcher: running jobs only
+    if (gate == 2 && (J.status == 0 || J.evaluated != 0)) return;            // quality: finished, once
+    const CloudView cvL = clouds[J.to_cloud];
+    const CloudView cvG = clouds[J.from_cloud];
+    extern __shared__ __align__(16) unsigned char item_smem_raw[];
+    ItemSmem& sm = *reinterpret_cast<ItemSmem*>(item_smem_raw);
+    const int tid = threadIdx.x;
+    if (bulk && (tid & 31) == 0)
+    {
+        mbar_init(&sm.sweep[tid >> 5].mbar[0], 1u);
+        mbar_init(&sm.sweep[tid >> 5].mbar[1], 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 12) sm.Rt[tid] = (tid < 9) ? J.R[tid] : J.t[tid - 9];
+    if (tid == 12) sm.grid = *cvG.grid;
+    if (tid == 13) sm.n_items = cvL.grid->n_items, sm.n_local = cvL.grid->n_valid;
+    __syncthreads();
+    const uint32_t n_items = (sm.grid.n_valid > 0) ? sm.n_items : 0u;
+    SeedRows       seed = {nullptr, seed_k};
+    if (seed_nn && J.rows_valid) seed.rows = seed_nn + (size_t)J.pair_base * seed_k;
+    for_each_item_sweep<K>(sm.sweep[tid >> 5], cvL, cvG, sm.grid, sm.Rt, n_items, sm.n_local, &J.next_item, cap_d2,
+                           bulk != 0, seed, [&](bool has, uint32_t pos, uint32_t orig, uint64_t (&key)[K], uint64_t sent) {
+                               epi(J, cvG, has, pos, orig, key, sent);
+                           });
+}
+
+// ---- the per-lane shell walk (tile_search.cuh) as the search stage: B200ICP_SEARCH=walk ------
+// Warps draw items from the job's counter (dynamic: the results do not depend
+// on who searches what, and items differ a lot in cost).  Per item (<= 32
+// queries, one per lane): box of the queries' home cells -> tile -> search.
+template <int K, class F>
+__device__ __forceinline__ void for_each_item(WarpTile& W, const CloudView& cvL, const CloudView& cvG,
+                                              const GridDev& grid, const double* Rt, uint32_t n_items,
+                                              uint32_t* next_item, float cap_d2, const SeedRows& seed, F&& f)
+{
+    const int lane = threadIdx.x & 31;
+    for (;;)
+    {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(next_item, 1u);
+        item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        if (item >= n_items) break;
+        const long long dbg_t0 = g_dbg_item_cycles ? clock64() : 0;
+        const uint32_t first = __ldg(cvL.item_first + item);
+        const uint32_t cnt = __ldg(cvL.item_first + item + 1) - first;
+        const bool     has = (uint32_t)lane < cnt;
+        float4         pl = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has) pl = __ldg(cvL.pts + first + lane);
+        double gx, gy, gz;
+        transform_point(Rt, pl, gx, gy, gz);
+        const float qx = (float)gx, qy = (float)gy, qz = (float)gz;
+        const bool  finite = has && (fabsf(qx) <= FLT_MAX) && (fabsf(qy) <= FLT_MAX) && (fabsf(qz) <= FLT_MAX);
+        // this lane's radius cap: the caller's, or the tighter bound of its seeds
+        float cap = cap_d2;
+        if (seed.rows && finite)
+            cap = seeded_cap<K>(cvG, seed.rows + (size_t)(first + lane) * seed.k, seed.k, qx, qy, qz, cap_d2);
+        // shells the widest lane of the item may need (warp-uniform)
+        float capmax = finite ? cap : 0.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) capmax = fmaxf(capmax, __shfl_xor_sync(0xFFFFFFFFu, capmax, o));
+        const int       S = search_shells(grid, capmax);
+        const QueryCell qc = locate_query(grid, S, qx, qy, qz);
+        const bool      hasq = has && qc.valid;
+        int lo[3] = {hasq ? qc.hx : INT_MAX, hasq ? qc.hy : INT_MAX, hasq ? qc.hz : INT_MAX};
+        int hi[3] = {hasq ? qc.hx : INT_MIN, hasq ? qc.hy : INT_MIN, hasq ? qc.hz : INT_MIN};
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+        {
+            lo[d] = __reduce_min_sync(0xFFFFFFFFu, lo[d]);
+            hi[d] = __reduce_max_sync(0xFFFFFFFFu, hi[d]);
+        }
+        TileGeom       G;
+        const bool     tiled = warp_tile_build(W, G, cvG, lo, hi, S);
+        const uint64_t sent = sentinel_key(cap);
+        uint64_t       key[K];
+#pragma unroll
+        for (int i = 0; i < K; i++) key[i] = sent;
+        if (hasq)
+        {
+            if (tiled)
+                tile_knn<K>(W, G, cvG, grid, qc, S, qx, qy, qz, key);
+            else
+                knn_search<K>(cvG, grid, qx, qy, qz, cap, key);
+        }
+        f(has, first + lane, __float_as_uint(pl.w), key, sent);
+        if (g_dbg_item_cycles && lane == 0)
+            g_dbg_item_cycles[item] = (uint32_t)min((long long)0x7FFFFFFF, clock64() - dbg_t0) | (tiled ? 0u : 0x80000000u);
 #ifdef B200ICP_DBG_COUNT
         if (g_dbg_lane_cand && g_dbg_item_cycles)
         {   // per item: max and sum over lanes of the candidates scanned
@@ -490,48 +577,43 @@ __device__ __forceinline__ void for_each_item(WarpTile& W, SweepSmem& SW, const 
             if (lane == 0) g_dbg_item_cycles[n_items + 1 + 2 * item] = mx, g_dbg_item_cycles[n_items + 2 + 2 * item] = sm;
         }
 #endif
-        item = __shfl_sync(full, nxt, 0);
     }
 }
 
 struct SearchSmem
 {
-    WarpTile  tile[kChunk / 32];
-    SweepSmem sweep[kChunk / 32];
-    GridDev   grid;
-    double    Rt[12];
-    uint32_t  n_items, n_local;
+    WarpTile tile[kChunk / 32];
+    GridDev  grid;
+    double   Rt[12];
+    uint32_t n_items;
 };
 
 // seed_nn / seed_k: the launch's neighbour-row buffer of an earlier matcher
 // search (rows of job j start at J.pair_base); used when the job says its rows
 // are valid (JobDev::rows_valid, set by the solver after a matcher run).
-// Dynamic shared memory: sizeof(SearchSmem) (launch_search_k opts in).
 #ifndef B200ICP_SEARCH_MINB
-#define B200ICP_SEARCH_MINB 3
+#define B200ICP_SEARCH_MINB 4
 #endif
 template <int K, class Epi>
 __global__ void __launch_bounds__(kChunk, B200ICP_SEARCH_MINB)
     search_tile_kernel(const CloudView* __restrict__ clouds, JobDev* __restrict__ jobs, IcpDevParams P,
-                       float cap_d2, int gate, const uint32_t* seed_nn, uint32_t seed_k, int sweep_on, Epi epi)
+                       float cap_d2, int gate, const uint32_t* seed_nn, uint32_t seed_k, Epi epi)
 {
     JobDev& J = jobs[blockIdx.y];
     if (gate == 1 && (J.status != 0 || !matcher_active(P, J.iter))) return;  // matcher: running jobs only
     if (gate == 2 && (J.status == 0 || J.evaluated != 0)) return;            // quality: finished, once
     const CloudView cvL = clouds[J.to_cloud];
     const CloudView cvG = clouds[J.from_cloud];
-    extern __shared__ __align__(16) unsigned char search_smem_raw[];
-    SearchSmem& sm = *reinterpret_cast<SearchSmem*>(search_smem_raw);
+    __shared__ SearchSmem sm;
     const int tid = threadIdx.x;
     if (tid < 12) sm.Rt[tid] = (tid < 9) ? J.R[tid] : J.t[tid - 9];
     if (tid == 12) sm.grid = *cvG.grid;
-    if (tid == 13) sm.n_items = cvL.grid->n_items, sm.n_local = cvL.grid->n_valid;
+    if (tid == 13) sm.n_items = cvL.grid->n_items;
     __syncthreads();
     const uint32_t n_items = (sm.grid.n_valid > 0) ? sm.n_items : 0u;
     SeedRows       seed = {nullptr, seed_k};
     if (seed_nn && J.rows_valid) seed.rows = seed_nn + (size_t)J.pair_base * seed_k;
-    for_each_item<K>(sm.tile[tid >> 5], sm.sweep[tid >> 5], cvL, cvG, sm.grid, sm.Rt, n_items, sm.n_local,
-                     &J.next_item, cap_d2, sweep_on != 0, seed,
+    for_each_item<K>(sm.tile[tid >> 5], cvL, cvG, sm.grid, sm.Rt, n_items, &J.next_item, cap_d2, seed,
                      [&](bool has, uint32_t pos, uint32_t orig, uint64_t (&key)[K], uint64_t sent) {
                          epi(J, cvG, has, pos, orig, key, sent);
                      });
@@ -1497,27 +1579,29 @@ static int wait_cloud(Workspace* ws, const b200icp_cloud* c)
     return B200ICP_OK;
 }
 
-// Switches (environment, read once): B200ICP_SEARCH=sweep selects the tile
-// sweep (sweep_search.cuh) as the search stage instead of the per-lane shell
-// walk (tile_search.cuh; measured faster on LiDAR scans);
-// B200ICP_WPI=1|2|4 the warps that share one item in the sweep.
+// Switches (environment, read once): the search stage is the per-lane shell walk
+// (tile_search.cuh); B200ICP_SEARCH=item selects the item sweep (item_sweep.cuh)
+// and B200ICP_SEARCH=sweep the radius-wide tile sweep (sweep_search.cuh) instead --
+// same results, measured slower on LiDAR scans, kept for A/B runs;
+// B200ICP_WPI=1|2|4 the warps that share one item in the tile sweep.
 struct SearchConfig
 {
     bool sweep = false;
     int  wpi = 0;  // 0 = automatic
     bool graphs = true;  // B200ICP_GRAPH=0: no CUDA-graph replay of single registrations
+    bool tma = false;    // B200ICP_TMA=1 (with B200ICP_SEARCH=item): runs staged with cp.async.bulk + mbarriers
     bool seeds = true;   // B200ICP_SEED=0: searches never take their bound from the previous neighbour rows
-    bool item_sweep = true;  // B200ICP_ITEM_SWEEP=0: every lane walks its shells alone (item_sweep.cuh off)
+    bool walk = true;    // the per-lane shell walk (tile_search.cuh); B200ICP_SEARCH=item: the item sweep (item_sweep.cuh)
 };
 static const SearchConfig& search_config()
 {
     static const SearchConfig cfg = [] {
         SearchConfig c;
-        if (const char* s = getenv("B200ICP_SEARCH")) c.sweep = (strcmp(s, "sweep") == 0);
+        if (const char* s = getenv("B200ICP_SEARCH")) c.sweep = (strcmp(s, "sweep") == 0), c.walk = (strcmp(s, "item") != 0) && !c.sweep;
         if (const char* w = getenv("B200ICP_WPI")) c.wpi = atoi(w);
         if (const char* g = getenv("B200ICP_GRAPH")) c.graphs = atoi(g) != 0;
         if (const char* g = getenv("B200ICP_SEED")) c.seeds = atoi(g) != 0;
-        if (const char* g = getenv("B200ICP_ITEM_SWEEP")) c.item_sweep = atoi(g) != 0;
+        if (const char* g = getenv("B200ICP_TMA")) c.tma = atoi(g) != 0;
         return c;
     }();
     return cfg;
@@ -1553,21 +1637,21 @@ static void launch_search_k(const ::b200icp* ctx, Workspace* ws, size_t max_poin
     cudaStream_t        s = ws->stream;
     const SearchConfig& cfg = search_config();
     const size_t        items = std::max<size_t>(1, (max_points + kItem - 1) / kItem);
-    if (!cfg.sweep)
+    if (!cfg.sweep && !cfg.walk)
     {
         // resident CTAs on one SM (registers and the opted-in dynamic shared memory); every instantiation opts in once
         static int  resident = 0;
         static bool opted = false;  // per instantiation of this template
-        const auto  kern = search_tile_kernel<K, Epi>;
+        const auto  kern = search_item_kernel<K, Epi>;
         if (!opted)
         {
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SearchSmem));
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ItemSmem));
             opted = true;
         }
         if (resident == 0)
         {
             int occ = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kChunk, sizeof(SearchSmem)) != cudaSuccess ||
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kChunk, sizeof(ItemSmem)) != cudaSuccess ||
                 occ < 1)
                 occ = 3;
             resident = occ;
@@ -1576,8 +1660,27 @@ static void launch_search_k(const ::b200icp* ctx, Workspace* ws, size_t max_poin
         const size_t   wave = (size_t)ctx->sm_count * resident;
         const size_t   cap = std::max<size_t>(4, (2 * wave + njobs - 1) / njobs);
         const uint32_t G = (uint32_t)std::max<size_t>(1, std::min({(items + warps - 1) / warps, cap, wave}));
-        kern<<<dim3(G, (unsigned)njobs), kChunk, sizeof(SearchSmem), s>>>(d_clouds, d_jobs, D, cap_d2, gate, seed_nn,
-                                                                         seed_k, cfg.item_sweep ? 1 : 0, epi);
+        kern<<<dim3(G, (unsigned)njobs), kChunk, sizeof(ItemSmem), s>>>(d_clouds, d_jobs, D, cap_d2, gate, seed_nn,
+                                                                       seed_k, cfg.tma ? 1 : 0, epi);
+    }
+    else if (cfg.walk)
+    {
+        // resident CTAs of the walk on one SM (registers and shared memory)
+        static int resident = 0;
+        if (resident == 0)
+        {
+            int occ = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_tile_kernel<6, NnWriter>, kChunk, 0) !=
+                    cudaSuccess || occ < 1)
+                occ = 4;
+            resident = occ;
+        }
+        const size_t   warps = kChunk / 32;
+        const size_t   wave = (size_t)ctx->sm_count * resident;
+        const size_t   cap = std::max<size_t>(4, (2 * wave + njobs - 1) / njobs);
+        const uint32_t G = (uint32_t)std::max<size_t>(1, std::min({(items + warps - 1) / warps, cap, wave}));
+        search_tile_kernel<K, Epi><<<dim3(G, (unsigned)njobs), kChunk, 0, s>>>(d_clouds, d_jobs, D, cap_d2, gate,
+                                                                              seed_nn, seed_k, epi);
     }
     else
     {
@@ -2164,10 +2267,10 @@ int run_knn(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, co
         B2_CUDA_TRY(cudaStreamSynchronize(s));
         B2_CUDA_TRY(cudaMemcpyFromSymbol(h, g_dbg_phase, sizeof(h)));
         B2_CUDA_TRY(cudaMemcpyToSymbol(g_dbg_phase, z, sizeof(z)));
-        fprintf(stderr, "[dbg phases] Mcycles: setup %.1f tile %.1f round0 %.1f enum %.1f sweep %.1f walk %.1f epi %.1f | "
-                        "loaded %llu kept %llu uncovered lanes %llu attempts %llu groups %llu\n",
+        fprintf(stderr, "[dbg phases] Mcycles: setup %.1f - %.1f - %.1f enum %.1f sweep %.1f alone %.1f epi %.1f | "
+                        "loaded %llu kept %llu lanes searched singly %llu passes %llu groups %llu alone %llu\n",
                 h[0] * 1e-6, h[1] * 1e-6, h[2] * 1e-6, h[3] * 1e-6, h[4] * 1e-6, h[5] * 1e-6, h[6] * 1e-6, h[8], h[9],
-                h[10], h[11], h[12]);
+                h[10], h[11], h[12], h[13]);
     }
 #endif
     if (d_dbg)

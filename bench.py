@@ -281,6 +281,24 @@ def knn_microbench(torch, icp, scans, poses, dev, peak):
         out.append({"case": name, "n_queries": nq, "n_ref": len(ref) if ref else len(cl[0]), "k": k,
                     "radius_m": 0.7, "kernel_ms": ms, "queries_per_s": qps,
                     "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak})
+    # uncapped (max_dist = +inf): the capped pass at the index radius plus the completion of the incomplete rows
+    # over the whole cloud (b200icp_knn, results to the host; the kernel time is the library's events around both)
+    try:
+        for k in (1, 6):
+            icp.knn(clouds[0], clouds[1], k, float("inf"))
+            icp.profile_reset()
+            for r in range(3):
+                idx_u, _ = icp.knn(clouds[r], clouds[r + 1], k, float("inf"))
+            pr = icp.profile()
+            ms = pr["knn_ms"] / max(pr["knn_launches"], 1)
+            qps = len(clouds[1]) / (ms * 1e-3)
+            out.append({"case": "120k_vs_120k_uncapped", "n_queries": len(clouds[1]), "n_ref": len(clouds[0]), "k": k,
+                        "radius_m": None, "kernel_ms": ms, "queries_per_s": qps,
+                        "algorithmic_GBps": qps * KNN_ALGO_BYTES[k] / 1e9,
+                        "frac_of_hbm_peak": qps * KNN_ALGO_BYTES[k] / 1e9 / peak,
+                        "rows_without_k_neighbours": int((idx_u[:, k - 1] == 0xFFFFFFFF).sum())})
+    except Exception as e:
+        out.append({"case": "120k_vs_120k_uncapped", "error": f"{type(e).__name__}: {e}"[:200]})
     # the same kernel on points uniform in a box (SURVEY 8d asks for both distributions): 120k x 120k in
     # 60 x 60 x 6 m, about 8 points within the 0.7 m radius of a query
     try:

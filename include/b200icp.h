@@ -181,12 +181,45 @@ int b200icp_voxel_decimate(b200icp_t* icp, const b200icp_cloud_t* in, float reso
                            int use_average, float search_radius, b200icp_cloud_t** out,
                            uint32_t* keep_idx);
 
+/* FilterEdgesPlanes on the device: the filter class the reference's parameter
+ * files name (params/kitti-default.yaml:21-32 `pointcloud_filter_class:
+ * mola::lidar_segmentation::FilterEdgesPlanes` + `pointcloud_filter_params`;
+ * defaults include/mola-fe-lidar/LidarOdometry.h:76-80), applied where the
+ * reference calls apply_filter_pipeline (LidarOdometry.cpp:223-224).  Per voxel
+ * of voxel_filter_resolution with at least min_points_per_voxel points: eigenvalues
+ * e0 <= e1 <= e2 of the covariance; e2 < max_e2_e0*e0 && e1 < max_e1_e0*e0 ->
+ * "edges"; else e2 > min_e2_e0*e0 && e1 > min_e1_e0*e0 and a normal that is not
+ * vertical (|n.z| < 0.9) -> "planes"; every voxel_filter_decimation-th point of
+ * a classified voxel joins its layer, every full_pointcloud_decimation-th point
+ * of every voxel joins "full_decim" (points in ascending original index). */
+typedef struct b200icp_edges_planes_params
+{
+    float    voxel_filter_resolution;    /* [m] (yaml:25) */
+    uint32_t full_pointcloud_decimation; /* yaml:27 */
+    uint32_t voxel_filter_decimation;    /* yaml:28 */
+    float    voxel_filter_max_e2_e0, voxel_filter_max_e1_e0; /* yaml:29-30 */
+    float    voxel_filter_min_e2_e0, voxel_filter_min_e1_e0; /* yaml:31-32 */
+    uint32_t min_points_per_voxel;       /* additive; 5 */
+} b200icp_edges_planes_params_t;
+/* The shipped values (kitti-default.yaml:23-32). */
+void b200icp_edges_planes_defaults(b200icp_edges_planes_params_t* p);
+/* layers_out[0..2] = new indexed clouds "edges", "planes", "full_decim" (each
+ * in ascending original index; free with b200icp_cloud_free).  layer_flags_out
+ * (optional, host, capacity = size of `in`): bit 0 edges, bit 1 planes, bit 2
+ * full_decim per input point.  n_classified_voxels_out: optional. */
+int b200icp_filter_edges_planes(b200icp_t* icp, const b200icp_cloud_t* in,
+                                const b200icp_edges_planes_params_t* params, float search_radius,
+                                b200icp_cloud_t* layers_out[3], uint8_t* layer_flags_out,
+                                uint32_t* n_classified_voxels_out);
+
 /* --- nearest neighbours (kdTreeNClosestPoint3DIdx behind the matchers) --- */
 /* For each point of `queries` moved by pose (x,y,z,yaw,pitch,roll; NULL =
  * identity): the k nearest points of `ref` with d2 <= max_dist^2, ascending by
  * (d2 as float32, index).  Outputs are host arrays [nq*k] in the queries'
  * ORIGINAL order, padded with B200ICP_INVALID_IDX / +inf.  max_dist must be
- * positive and finite (radius-capped search). */
+ * positive; +infinity = uncapped search: the capped pass at the radius `ref` was
+ * indexed for, then the rows still short of k neighbours are completed exactly
+ * over the whole cloud (one warp per query). */
 int b200icp_knn(b200icp_t* icp, const b200icp_cloud_t* ref, const b200icp_cloud_t* queries,
                 const double* pose6, uint32_t k, float max_dist, uint32_t* idx_out,
                 float* d2_out);

@@ -107,7 +107,7 @@ EXPORTS = [
     "b200icp_get_params", "b200icp_device", "b200icp_cloud_upload", "b200icp_cloud_upload_raw",
     "b200icp_cloud_from_device",
     "b200icp_cloud_free", "b200icp_cloud_size", "b200icp_cloud_device_bytes", "b200icp_cloud_download",
-    "b200icp_voxel_decimate", "b200icp_knn", "b200icp_knn_keys_device", "b200icp_merge_keys_device",
+    "b200icp_voxel_decimate", "b200icp_edges_planes_defaults", "b200icp_filter_edges_planes", "b200icp_knn", "b200icp_knn_keys_device", "b200icp_merge_keys_device",
     "b200icp_knn_keys_scatter", "b200icp_peer_alloc", "b200icp_peer_free", "b200icp_peer_open",
     "b200icp_peer_close", "b200icp_peer_barrier", "b200icp_knn_keys_exchange", "b200icp_fill_no_key",
     "b200icp_match", "b200icp_align", "b200icp_align_with", "b200icp_call_params_of",
@@ -153,6 +153,10 @@ def lib():
     L.b200icp_cloud_device_bytes.restype = C.c_size_t
     L.b200icp_cloud_download.argtypes = [vp, fp, fp, fp]
     L.b200icp_voxel_decimate.argtypes = [vp, vp, C.c_float, C.c_int, C.c_float, C.POINTER(vp), up]
+    L.b200icp_edges_planes_defaults.argtypes = [C.POINTER(EdgesPlanesParams)]
+    L.b200icp_edges_planes_defaults.restype = None
+    L.b200icp_filter_edges_planes.argtypes = [vp, vp, C.POINTER(EdgesPlanesParams), C.c_float, C.POINTER(vp * 3),
+                                              C.POINTER(C.c_uint8), C.POINTER(C.c_uint32)]
     L.b200icp_knn.argtypes = [vp, vp, vp, dp, C.c_uint32, C.c_float, up, fp]
     L.b200icp_knn_keys_device.argtypes = [vp, vp, vp, dp, C.c_uint32, C.c_float, vp, vp]
     L.b200icp_merge_keys_device.argtypes = [vp, vp, C.c_uint32, C.c_size_t, C.c_size_t, C.c_uint32, vp]
@@ -218,6 +222,14 @@ def params_from_yaml(text):
     p = Params()
     _check(lib().b200icp_params_from_yaml(text.encode(), C.byref(p)))
     return p
+
+
+class EdgesPlanesParams(C.Structure):
+    """b200icp_edges_planes_params_t (include/b200icp.h)."""
+    _fields_ = [("voxel_filter_resolution", C.c_float), ("full_pointcloud_decimation", C.c_uint32),
+                ("voxel_filter_decimation", C.c_uint32), ("voxel_filter_max_e2_e0", C.c_float),
+                ("voxel_filter_max_e1_e0", C.c_float), ("voxel_filter_min_e2_e0", C.c_float),
+                ("voxel_filter_min_e1_e0", C.c_float), ("min_points_per_voxel", C.c_uint32)]
 
 
 class Cloud:
@@ -318,6 +330,22 @@ class ICP:
         if want_indices:
             return out, keep[:len(out)].copy()
         return out
+
+    def filter_edges_planes(self, cloud, search_radius=0.0, **kw):
+        """FilterEdgesPlanes: (edges, planes, full_decim) clouds, per-point layer flags (bit 0 / 1 / 2) and the
+        number of classified voxels; keyword arguments override the shipped parameter values."""
+        prm = EdgesPlanesParams()
+        lib().b200icp_edges_planes_defaults(C.byref(prm))
+        for k, v in kw.items():
+            if not hasattr(prm, k):
+                raise TypeError(f"unknown FilterEdgesPlanes parameter {k}")
+            setattr(prm, k, v)
+        hs = (C.c_void_p * 3)()
+        flags = np.zeros(max(len(cloud), 1), dtype=np.uint8)
+        nv = C.c_uint32(0)
+        _check(lib().b200icp_filter_edges_planes(self.h, cloud.h, C.byref(prm), search_radius, C.byref(hs),
+                                                 _ptr(flags, C.c_uint8), C.byref(nv)))
+        return [Cloud(self, C.c_void_p(h)) for h in hs], flags[:len(cloud)], int(nv.value)
 
     # ---- search / matching / registration
     def knn(self, ref, queries, k, max_dist, pose6=None):

@@ -2196,6 +2196,94 @@ static int single_job_setup(Workspace* ws, const b200icp_cloud* from, const b200
     return B200ICP_OK;
 }
 
+// Uncapped search (max_dist = +inf), second pass: the rows the radius-capped search left incomplete -- queries with
+// fewer than k points within the index's block edge -- are completed EXACTLY by one warp per query over the whole
+// reference cloud: lane l takes every 32nd group of 8 sorted points, tests the group's box against the best bound
+// the warp has (the smallest k-th-best any lane holds: that lane alone has k points within it) and evaluates the
+// groups that survive; the 32 sorted lists are merged with k warp minima.  Same keys, same tie rule.
+template <int K>
+__global__ void __launch_bounds__(256)
+    knn_complete_kernel(const CloudView* __restrict__ clouds, const JobDev* __restrict__ jobs, uint32_t k,
+                        uint32_t* __restrict__ idx, float* __restrict__ d2)
+{
+    const JobDev&   J = jobs[0];
+    const CloudView cvL = clouds[J.to_cloud];
+    const CloudView cvG = clouds[J.from_cloud];
+    const uint32_t  nq = cvL.grid->n_valid, nr = cvG.grid->n_valid;
+    const int       lane = threadIdx.x & 31;
+    const unsigned  full = 0xFFFFFFFFu;
+    const uint32_t  warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t  kk_need = min(k, nr);
+    double          Rt[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) Rt[i] = (i < 9) ? J.R[i] : J.t[i - 9];
+    for (uint32_t pos = warp; pos < nq; pos += nwarps)
+    {
+        const float4   pl = __ldg(cvL.pts + pos);
+        const uint32_t orig = __float_as_uint(pl.w);
+        if (kk_need == 0 || idx[(size_t)orig * k + (kk_need - 1)] != kInvalid) continue;  // complete already (uniform)
+        double gx, gy, gz;
+        transform_point(Rt, pl, gx, gy, gz);
+        const float qx = (float)gx, qy = (float)gy, qz = (float)gz;
+        if (!((fabsf(qx) <= FLT_MAX) && (fabsf(qy) <= FLT_MAX) && (fabsf(qz) <= FLT_MAX))) continue;
+        const uint64_t sent = sentinel_key(INFINITY);
+        uint64_t       key[K];
+#pragma unroll
+        for (int i = 0; i < K; i++) key[i] = sent;
+        const uint32_t ngroups = (nr + kGroup - 1) / kGroup;
+        float          bound = INFINITY;  // warp-wide bound of the k-th neighbour (k = the launch's K here)
+        for (uint32_t g0 = 0; g0 < ngroups; g0 += 32)
+        {
+            const uint32_t g = g0 + lane;
+            if (g < ngroups)
+            {
+                const float4 lo = __ldg(cvG.gbox + 2 * g), hi = __ldg(cvG.gbox + 2 * g + 1);
+                if (!(box_lower_d2(qx, qy, qz, lo, hi) > fminf(bound, key_d2(key[K - 1]))))
+                {
+                    const uint32_t base = g * kGroup;
+#pragma unroll
+                    for (int u = 0; u < kGroup; u++)
+                        if (base + u < nr)
+                        {
+                            const float4   c = __ldg(cvG.pts + base + u);
+                            const uint64_t kk = make_key(dist2(qx, qy, qz, c), __float_as_uint(c.w));
+                            if (kk < key[K - 1]) topk_insert<K>(key, kk);
+                        }
+                }
+            }
+            // a lane whose list is full bounds the k-th neighbour of the union (ties: the bound is not strict)
+            bound = __uint_as_float(__reduce_min_sync(full, __float_as_uint(key_d2(key[K - 1]))));
+        }
+        // merge: the smallest head of the 32 sorted lists, K times (keys are unique: they hold the point's index)
+        uint64_t res[K];
+#pragma unroll
+        for (int i = 0; i < K; i++)
+        {
+            const uint32_t hi = __reduce_min_sync(full, (uint32_t)(key[0] >> 32));
+            const uint32_t lo = __reduce_min_sync(full, ((uint32_t)(key[0] >> 32) == hi) ? (uint32_t)key[0] : 0xFFFFFFFFu);
+            const uint64_t m = ((uint64_t)hi << 32) | lo;
+            res[i] = m;
+            if (key[0] == m && m != sent)
+            {
+#pragma unroll
+                for (int j = 0; j + 1 < K; j++) key[j] = key[j + 1];
+                key[K - 1] = sent;
+            }
+        }
+        if (lane == 0)
+        {
+#pragma unroll
+            for (int i = 0; i < K; i++)
+                if ((uint32_t)i < k)
+                {
+                    const bool ok = res[i] != sent;
+                    idx[(size_t)orig * k + i] = ok ? key_idx(res[i]) : kInvalid;
+                    if (d2) d2[(size_t)orig * k + i] = ok ? key_d2(res[i]) : INFINITY;
+                }
+        }
+    }
+}
+
 int run_knn(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, const double* pose6,
             uint32_t k, float max_dist, uint32_t* idx_out, float* d2_out)
 {
@@ -2204,11 +2292,14 @@ int run_knn(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, co
         set_error("k=%u outside [1,%d]", k, B200ICP_MAX_KNN);
         return B200ICP_ERR_BAD_ARG;
     }
-    if (!(max_dist > 0) || !std::isfinite(max_dist))
+    if (!(max_dist > 0))  // NaN included
     {
-        set_error("max_dist must be positive and finite (radius-capped search)");
+        set_error("max_dist must be positive (+inf = uncapped search)");
         return B200ICP_ERR_BAD_ARG;
     }
+    // uncapped: the capped search at the reference index's own radius first, the incomplete rows completed after
+    const bool uncapped = std::isinf(max_dist);
+    if (uncapped) max_dist = ref->cell_req / 1.002f;  // the radius the reference cloud was indexed for
     Lease L(ctx);
     if (!L.ws) return B200ICP_ERR_CUDA;
     Workspace*   ws = L.ws;
@@ -2259,6 +2350,19 @@ int run_knn(::b200icp* ctx, const b200icp_cloud* ref, const b200icp_cloud* q, co
         launch_search_k<6>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
     else
         launch_search_k<8>(ctx, ws, nq, 1, sj.d_clouds, sj.d_jobs, ctx->D, cap_d2, 0, w);
+    if (uncapped)
+    {
+        const int grid = ctx->sm_count * 8;
+        if (k == 1)
+            knn_complete_kernel<1><<<grid, 256, 0, s>>>(sj.d_clouds, sj.d_jobs, k, d_idx, d_d2);
+        else if (k <= 4)
+            knn_complete_kernel<4><<<grid, 256, 0, s>>>(sj.d_clouds, sj.d_jobs, k, d_idx, d_d2);
+        else if (k <= 6)
+            knn_complete_kernel<6><<<grid, 256, 0, s>>>(sj.d_clouds, sj.d_jobs, k, d_idx, d_d2);
+        else
+            knn_complete_kernel<8><<<grid, 256, 0, s>>>(sj.d_clouds, sj.d_jobs, k, d_idx, d_d2);
+        ws->launches++;
+    }
     if (prof) B2_CUDA_TRY(cudaEventRecord(ws->prof_ev[1], s));
     B2_CUDA_TRY(cudaGetLastError());
 #ifdef B200ICP_DBG_PHASES

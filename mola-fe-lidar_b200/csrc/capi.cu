@@ -246,6 +246,31 @@ extern "C" int b200icp_voxel_decimate(b200icp_t* icp, const b200icp_cloud_t* in,
     return run_voxel(icp, in, resolution, use_average, search_radius, out, keep_idx);
 }
 
+extern "C" void b200icp_edges_planes_defaults(b200icp_edges_planes_params_t* p)
+{
+    if (!p) return;
+    p->voxel_filter_resolution = 1.0f;  // params/kitti-default.yaml:25-32
+    p->full_pointcloud_decimation = 10;
+    p->voxel_filter_decimation = 10;
+    p->voxel_filter_max_e2_e0 = 30.f, p->voxel_filter_max_e1_e0 = 30.f;
+    p->voxel_filter_min_e2_e0 = 80.f, p->voxel_filter_min_e1_e0 = 80.f;
+    p->min_points_per_voxel = 5;
+}
+
+extern "C" int b200icp_filter_edges_planes(b200icp_t* icp, const b200icp_cloud_t* in,
+                                           const b200icp_edges_planes_params_t* params, float search_radius,
+                                           b200icp_cloud_t* layers_out[3], uint8_t* layer_flags_out,
+                                           uint32_t* n_classified_voxels_out)
+{
+    if (!icp || !in || !params || !layers_out)
+    {
+        set_error("null argument");
+        return B200ICP_ERR_BAD_ARG;
+    }
+    layers_out[0] = layers_out[1] = layers_out[2] = nullptr;
+    return run_edges_planes(icp, in, params, search_radius, layers_out, layer_flags_out, n_classified_voxels_out);
+}
+
 extern "C" int b200icp_knn(b200icp_t* icp, const b200icp_cloud_t* ref, const b200icp_cloud_t* queries,
                            const double* pose6, uint32_t k, float max_dist, uint32_t* idx_out,
                            float* d2_out)

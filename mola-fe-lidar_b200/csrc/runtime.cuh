@@ -241,6 +241,9 @@ int run_match(::b200icp* ctx, const b200icp_cloud* from, const b200icp_cloud* to
 int run_voxel(::b200icp* ctx, const b200icp_cloud* in, float resolution, int use_average,
               float search_radius, b200icp_cloud** out, uint32_t* keep_idx);
 
+int run_edges_planes(::b200icp* ctx, const b200icp_cloud* in, const b200icp_edges_planes_params_t* prm,
+                     float search_radius, b200icp_cloud** out3, uint8_t* layer_out, uint32_t* n_voxels_out);
+
 // sharded maps over the GPUs of one box (sharded.inl); the library owns the NCCL communicator
 int  run_comm_unique_id(unsigned char* id_out);
 int  run_comm_create(::b200icp* ctx, const unsigned char* id_bytes, int world, int rank, b200icp_comm** out);

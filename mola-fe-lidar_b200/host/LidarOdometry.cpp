@@ -176,6 +176,7 @@ void LidarOdometry::initialize(const Yaml& c)
         }
     }
     params_.voxel_decimation_resolution = 0.0;
+    params_.edges_planes_enabled = false;
     const Yaml& flt = cfg["pointcloud_filter"];
     if (!flt.isNull())
     {
@@ -183,12 +184,36 @@ void LidarOdometry::initialize(const Yaml& c)
         for (const auto& f : flt.seq)
         {
             const std::string cls = f.at("class_name").as_string();
-            if (cls != "mp2p_icp_filters::FilterDecimateVoxels")
+            const Yaml&       p = f.at("params");
+            if (cls == "mp2p_icp_filters::FilterDecimateVoxels")
+            {
+                p.load_req("voxel_filter_resolution", params_.voxel_decimation_resolution);
+                p.load_opt("use_voxel_average", params_.voxel_use_average);
+            }
+            else if (cls == "mp2p_icp_filters::FilterEdgesPlanes" || cls == "mola::lidar_segmentation::FilterEdgesPlanes")
+            {   // keys of pointcloud_filter_params (kitti-default.yaml:23-32); defaults = the shipped values
+                auto& e = params_.edges_planes;
+                b200icp_edges_planes_defaults(&e);
+                p.load_opt("voxel_filter_resolution", e.voxel_filter_resolution);
+                p.load_opt("full_pointcloud_decimation", e.full_pointcloud_decimation);
+                p.load_opt("voxel_filter_decimation", e.voxel_filter_decimation);
+                p.load_opt("voxel_filter_max_e2_e0", e.voxel_filter_max_e2_e0);
+                p.load_opt("voxel_filter_max_e1_e0", e.voxel_filter_max_e1_e0);
+                p.load_opt("voxel_filter_min_e2_e0", e.voxel_filter_min_e2_e0);
+                p.load_opt("voxel_filter_min_e1_e0", e.voxel_filter_min_e1_e0);
+                p.load_opt("b200_min_points_per_voxel", e.min_points_per_voxel);
+                std::string layer = "planes";
+                p.load_opt("b200_register_layer", layer);
+                if (layer == "edges") params_.edges_planes_layer = 0;
+                else if (layer == "planes") params_.edges_planes_layer = 1;
+                else if (layer == "full_decim") params_.edges_planes_layer = 2;
+                else throw std::runtime_error("b200_register_layer must be edges, planes or full_decim");
+                params_.edges_planes_enabled = true;
+            }
+            else
                 throw std::runtime_error("pointcloud_filter class_name=`" + cls +
-                                         "` is not registered (known: mp2p_icp_filters::FilterDecimateVoxels)");
-            const Yaml& p = f.at("params");
-            p.load_req("voxel_filter_resolution", params_.voxel_decimation_resolution);
-            p.load_opt("use_voxel_average", params_.voxel_use_average);
+                                         "` is not registered (known: mp2p_icp_filters::FilterDecimateVoxels, "
+                                         "mp2p_icp_filters::FilterEdgesPlanes)");
         }
     }
     // attach to world model, if present (cpp:144-146): the harness may have
@@ -264,7 +289,7 @@ DeviceCloud::Ptr LidarOdometry::make_cloud(const CObservation& o)
 {
     b200icp_t*       ctx = params_.icp.at(AlignKind::LidarOdometry).icp;
     b200icp_cloud_t* raw = nullptr;
-    const bool       filtered = params_.voxel_decimation_resolution > 0;
+    const bool       filtered = params_.voxel_decimation_resolution > 0 || params_.edges_planes_enabled;
     {   // observation -> device cloud (apply_generators, cpp:215-217); the search index is built for the cloud
         // that gets registered: this one, or the output of the filter stage below
         ProfilerEntry tle0(profiler_, "doProcessNewObservation.0.upload_and_index");
@@ -276,6 +301,16 @@ DeviceCloud::Ptr LidarOdometry::make_cloud(const CObservation& o)
     }
     auto              raw_ptr = std::make_shared<DeviceCloud>(raw, ctx, cloud_search_radius_);
     ProfilerEntry     tle1(profiler_, "doProcessNewObservation.1.filter_pointclouds");
+    if (params_.edges_planes_enabled)
+    {   // FilterEdgesPlanes: three layers on the device; the configured one is what gets registered
+        b200icp_cloud_t* layers[3] = {nullptr, nullptr, nullptr};
+        check_rc(b200icp_filter_edges_planes(ctx, raw, &params_.edges_planes, cloud_search_radius_, layers, nullptr,
+                                             nullptr),
+                 "b200icp_filter_edges_planes");
+        for (int l = 0; l < 3; l++)
+            if (l != params_.edges_planes_layer) b200icp_cloud_free(layers[l]);
+        return std::make_shared<DeviceCloud>(layers[params_.edges_planes_layer], ctx, cloud_search_radius_);
+    }
     if (filtered)
     {
         b200icp_cloud_t* dec = nullptr;

@@ -120,6 +120,12 @@ class LidarOdometry : public FrontEndBase
          *  decimation stage, 0 = empty pipeline */
         double voxel_decimation_resolution{0.0};
         bool   voxel_use_average{false};
+        /** `pointcloud_filter: - class_name: mp2p_icp_filters::FilterEdgesPlanes` (the class the reference's stale
+         * keys name, kitti-default.yaml:21-32): its parameters, and which of its output layers is registered
+         * (additive key b200_register_layer: edges | planes | full_decim). */
+        bool                          edges_planes_enabled{false};
+        b200icp_edges_planes_params_t edges_planes{};
+        int                           edges_planes_layer{1};
         /** seed of the Monte-Carlo guesses (the reference default-constructs
          *  an unseeded generator, cpp:773) */
         uint64_t montecarlo_seed{1};

@@ -1276,3 +1276,99 @@ size_t orc_voxel_decimate(const float* x, const float* y, const float* z, size_t
     free(tab), free(slot_of);
     return m;
 }
+
+/* ----------------------------------------------------------------- A.13 */
+/* FilterEdgesPlanes (the class the reference's stale keys name,
+ * params/kitti-default.yaml:21-32, LidarOdometry.h:76-80).  The filter body
+ * lives in mp2p_icp_filters (absent, unpinned): this is a restatement of its
+ * published behaviour, NORMATIVE for this repo where upstream is uncertain:
+ *   voxel key as A.11 (f32 division, floor); per voxel with >= min_points
+ *   points: mean and covariance (1/n) in f64, points taken in ascending
+ *   original index, eigenvalues e0 <= e1 <= e2 and the eigenvector v0 of e0
+ *   by the cyclic Jacobi of row J;
+ *     e2 < max_e2_e0 * e0 && e1 < max_e1_e0 * e0            -> "edges"
+ *     else e2 > min_e2_e0 * e0 && e1 > min_e1_e0 * e0
+ *          && |v0.z| < 0.9 (ground-like planes are dropped)  -> "planes"
+ *   every voxel_decimation-th point of a classified voxel (t = 0, d, 2d, ...
+ *   in ascending original index) joins the class layer; every
+ *   full_decimation-th point of EVERY voxel joins "full_decim".
+ * layer[i]: bit 0 edges, bit 1 planes, bit 2 full_decim.  Returns the number of
+ * classified voxels. */
+typedef struct
+{
+    uint64_t key;
+    uint32_t idx;
+} ep_rec;
+static int ep_cmp(const void* a, const void* b)
+{
+    const ep_rec *x = (const ep_rec*)a, *y = (const ep_rec*)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0);
+}
+size_t orc_filter_edges_planes(const float* x, const float* y, const float* z, size_t n, float resolution,
+                               uint32_t full_decimation, uint32_t voxel_decimation, float max_e2_e0,
+                               float max_e1_e0, float min_e2_e0, float min_e1_e0, uint32_t min_points,
+                               uint8_t* layer)
+{
+    if (!n) return 0;
+    if (full_decimation < 1) full_decimation = 1;
+    if (voxel_decimation < 1) voxel_decimation = 1;
+    ep_rec* rec = (ep_rec*)malloc(sizeof(ep_rec) * n);
+    size_t  m = 0;
+    for (size_t i = 0; i < n; i++)
+    {
+        layer[i] = 0;
+        if (!(isfinite(x[i]) && isfinite(y[i]) && isfinite(z[i]))) continue;
+        const float fx = floorf(x[i] / resolution), fy = floorf(y[i] / resolution), fz = floorf(z[i] / resolution);
+        if (!(fabsf(fx) <= 1048575.0f) || !(fabsf(fy) <= 1048575.0f) || !(fabsf(fz) <= 1048575.0f)) continue;
+        rec[m].key = (uint64_t)((int32_t)fx + 1048576) | ((uint64_t)((int32_t)fy + 1048576) << 21) |
+                     ((uint64_t)((int32_t)fz + 1048576) << 42);
+        rec[m].idx = (uint32_t)i;
+        m++;
+    }
+    qsort(rec, m, sizeof(ep_rec), ep_cmp);
+    size_t classified = 0;
+    for (size_t a = 0; a < m;)
+    {
+        size_t b = a;
+        while (b < m && rec[b].key == rec[a].key) b++;
+        const size_t cnt = b - a;
+        uint8_t      cls = 0;
+        if (cnt >= min_points && cnt >= 1)
+        {
+            double sx = 0, sy = 0, sz = 0;
+            for (size_t j = a; j < b; j++)
+                sx += (double)x[rec[j].idx], sy += (double)y[rec[j].idx], sz += (double)z[rec[j].idx];
+            const double inv = 1.0 / (double)cnt;
+            const double cx = sx * inv, cy = sy * inv, cz = sz * inv;
+            double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
+            for (size_t j = a; j < b; j++)
+            {
+                const double dx = (double)x[rec[j].idx] - cx, dy = (double)y[rec[j].idx] - cy,
+                             dz = (double)z[rec[j].idx] - cz;
+                c00 += dx * dx, c01 += dx * dy, c02 += dx * dz;
+                c11 += dy * dy, c12 += dy * dz, c22 += dz * dz;
+            }
+            double C[9] = {c00 * inv, c01 * inv, c02 * inv, c01 * inv, c11 * inv, c12 * inv, c02 * inv, c12 * inv, c22 * inv};
+            double ev[3], V[9];
+            jacobi_sym(3, C, ev, V);
+            const double e0 = ev[0], e1 = ev[1], e2 = ev[2];
+            if (e2 < (double)max_e2_e0 * e0 && e1 < (double)max_e1_e0 * e0)
+                cls = 1;
+            else if (e2 > (double)min_e2_e0 * e0 && e1 > (double)min_e1_e0 * e0 && fabs(V[6]) < 0.9)
+                cls = 2; /* V[6] = z component of the first column (eigenvector of e0) */
+            if (cls) classified++;
+        }
+        for (size_t j = a; j < b; j++)
+        {
+            const size_t t = j - a;
+            uint8_t      f = 0;
+            if (cls && (t % voxel_decimation) == 0) f |= cls;
+            if ((t % full_decimation) == 0) f |= 4;
+            layer[rec[j].idx] = f;
+        }
+        a = b;
+    }
+    free(rec);
+    return classified;
+}

@@ -165,6 +165,13 @@ size_t orc_voxel_decimate(const float* x, const float* y, const float* z, size_t
                           float resolution, int use_average, uint32_t* keep_idx, float* ox,
                           float* oy, float* oz);
 
+/* A.13 FilterEdgesPlanes (normative restatement, see icp_oracle.c): layer[i] bit 0 "edges", bit 1 "planes",
+ * bit 2 "full_decim".  Returns the number of classified voxels. */
+size_t orc_filter_edges_planes(const float* x, const float* y, const float* z, size_t n, float resolution,
+                               uint32_t full_decimation, uint32_t voxel_decimation, float max_e2_e0,
+                               float max_e1_e0, float min_e2_e0, float min_e1_e0, uint32_t min_points,
+                               uint8_t* layer);
+
 #ifdef __cplusplus
 }
 #endif

@@ -112,6 +112,9 @@ def lib():
     L.orc_icp_align.restype = C.c_int
     L.orc_voxel_decimate.argtypes = [fp, fp, fp, C.c_size_t, C.c_float, C.c_int, up, fp, fp, fp]
     L.orc_voxel_decimate.restype = C.c_size_t
+    L.orc_filter_edges_planes.argtypes = [fp, fp, fp, C.c_size_t, C.c_float, C.c_uint32, C.c_uint32, C.c_float,
+                                          C.c_float, C.c_float, C.c_float, C.c_uint32, C.POINTER(C.c_uint8)]
+    L.orc_filter_edges_planes.restype = C.c_size_t
     _lib = L
     return L
 
@@ -316,3 +319,23 @@ def voxel_decimate(xyz, resolution, use_average=False):
                                  C.c_float(resolution), int(use_average), _p(keep, C.c_uint32),
                                  _p(ox, C.c_float), _p(oy, C.c_float), _p(oz, C.c_float))
     return keep[:m].copy(), np.stack([ox[:m], oy[:m], oz[:m]], axis=1)
+
+
+EDGES_PLANES_DEFAULTS = dict(voxel_filter_resolution=1.0, full_pointcloud_decimation=10, voxel_filter_decimation=10,
+                             voxel_filter_max_e2_e0=30.0, voxel_filter_max_e1_e0=30.0, voxel_filter_min_e2_e0=80.0,
+                             voxel_filter_min_e1_e0=80.0, min_points_per_voxel=5)  # params/kitti-default.yaml:23-32
+
+
+def filter_edges_planes(xyz, **kw):
+    """A.13: per-point layer flags (bit 0 edges, bit 1 planes, bit 2 full_decim) and the classified voxel count."""
+    p = dict(EDGES_PLANES_DEFAULTS, **kw)
+    xyz = np.asarray(xyz, dtype=np.float32).reshape(-1, 3)
+    x, y, z = _f32(xyz[:, 0]), _f32(xyz[:, 1]), _f32(xyz[:, 2])
+    layer = np.zeros(len(x), dtype=np.uint8)
+    nv = lib().orc_filter_edges_planes(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float), len(x),
+                                       p["voxel_filter_resolution"], p["full_pointcloud_decimation"],
+                                       p["voxel_filter_decimation"], p["voxel_filter_max_e2_e0"],
+                                       p["voxel_filter_max_e1_e0"], p["voxel_filter_min_e2_e0"],
+                                       p["voxel_filter_min_e1_e0"], p["min_points_per_voxel"],
+                                       _p(layer, C.c_uint8))
+    return layer, int(nv)

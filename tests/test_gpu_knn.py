@@ -109,3 +109,24 @@ def test_lidar_scan_full_size(icp, oracle):
     guess = scene.relative_pose6(poses[0], poses[1])
     _check(icp, oracle, scans[0], scans[1], 6, 0.7, pose=guess, kdtree=True)
     _check(icp, oracle, scans[0], scans[1], 1, 0.1, pose=guess, kdtree=True)
+
+
+@pytest.mark.parametrize("k", [1, 6, 8])
+def test_uncapped(icp, oracle, rng, k):
+    """max_dist = +inf (SURVEY 8d 'radius cap 0.7 m and uncapped'): rows the radius-capped pass leaves incomplete are
+    completed over the whole reference cloud; queries far outside the cloud, duplicates and exact ties included."""
+    centres = rng.uniform(-20, 20, size=(20, 3))
+    ref = (centres[rng.integers(0, 20, 5000)] + rng.normal(0, 0.3, size=(5000, 3))).astype(np.float32)
+    ref[200:260] = ref[7]
+    qry = np.concatenate([ref[::9], rng.uniform(-60, 60, size=(1500, 3)).astype(np.float32),
+                          np.array([[1e4, -1e4, 3e3], [0, 0, 0]], dtype=np.float32)])
+    _check(icp, oracle, ref, qry, k, np.inf)
+    g = np.arange(-4, 5, dtype=np.float32) * 2.0   # lattice coarser than the index radius: every row needs pass 2
+    lat = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    _check(icp, oracle, lat, np.concatenate([lat[::3] + np.float32(1.0), lat[::7]]), k, np.inf)
+
+
+def test_uncapped_fewer_points_than_k(icp, oracle, rng):
+    ref = rng.uniform(-1, 1, size=(4, 3))
+    qry = rng.uniform(-30, 30, size=(100, 3))
+    _check(icp, oracle, ref, qry, 6, np.inf)

@@ -218,3 +218,31 @@ def test_golden_vectors(oracle):
     assert np.allclose(r["pose"], meta["pose"], atol=1e-9)
     assert r["n_iterations"] == meta["n_iterations"] and r["n_pairings"] == meta["n_pairings"]
     assert abs(r["quality"] - meta["quality"]) < 1e-12
+
+
+def test_filter_edges_planes_known_answers(oracle, rng):
+    """A.13 on shapes whose class is known: a vertical wall is 'planes', a horizontal one is dropped (ground-like),
+    an isotropic blob is 'edges', a thin line is neither (e2 >> e0 but e1 ~ e0), a voxel below the point minimum is
+    only in full_decim; decimation takes every d-th point of a voxel in ascending original index."""
+    def one(pts, **kw):
+        f, nv = oracle.filter_edges_planes(np.asarray(pts, dtype=np.float32), **kw)
+        return f, nv
+    wall = np.c_[rng.uniform(0.01, 0.99, 200), 0.5 + rng.normal(0, 1e-3, 200), rng.uniform(0.01, 0.99, 200)]
+    f, nv = one(wall, voxel_filter_decimation=1, full_pointcloud_decimation=1)
+    assert nv == 1 and (f == 6).all()
+    ground = wall[:, [0, 2, 1]]
+    f, nv = one(ground, voxel_filter_decimation=1, full_pointcloud_decimation=1)
+    assert nv == 0 and (f == 4).all()
+    blob = rng.uniform(0.01, 0.99, (200, 3))
+    f, nv = one(blob, voxel_filter_decimation=1, full_pointcloud_decimation=1)
+    assert nv == 1 and (f == 5).all()
+    line = np.c_[rng.uniform(0.01, 0.99, 200), 0.5 + rng.normal(0, 1e-3, 200), 0.5 + rng.normal(0, 1e-3, 200)]
+    f, nv = one(line, voxel_filter_decimation=1, full_pointcloud_decimation=1)
+    assert nv == 0 and (f == 4).all()
+    f, nv = one(blob[:4], voxel_filter_decimation=1, full_pointcloud_decimation=1)
+    assert nv == 0 and (f == 4).all()
+    f, nv = one(blob, voxel_filter_decimation=10, full_pointcloud_decimation=7)
+    assert np.array_equal(np.flatnonzero(f & 1), np.arange(0, 200, 10))
+    assert np.array_equal(np.flatnonzero(f & 4), np.arange(0, 200, 7))
+    f, nv = one(np.array([[np.nan, 0, 0], [0.5, 0.5, 0.5]]))
+    assert f[0] == 0 and f[1] == 4

@@ -7,7 +7,7 @@ EXTRA="$*"
 cd "$(dirname "$0")/../mola-fe-lidar_b200"
 B=build/var/$NAME; mkdir -p $B lib
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC,-ffp-contract=off,-Wall --expt-relaxed-constexpr -I../include $EXTRA"
-for f in runtime cloud align voxel capi; do
+for f in runtime cloud align voxel edges_planes capi; do
   /usr/local/cuda/bin/nvcc $FLAGS -Xptxas -v -c csrc/$f.cu -o $B/$f.o 2> $B/$f.log &
 done
 /usr/local/cuda/bin/nvcc $FLAGS -x cu -c csrc/icp_params_yaml.cpp -o $B/icp_params_yaml.o 2> $B/yaml.log &

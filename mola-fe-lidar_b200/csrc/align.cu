@@ -1271,7 +1271,10 @@ __device__ void solve_job_warp(JobDev& J, SolveSmem& ss, const IcpDevParams& P, 
         }
         __syncwarp();
         inner++;
-        if (ss.stop) break;
+        // every lane takes its copy before lane 0 may reuse ss.stop below (racecheck: read here / write after the loop)
+        const int stop_now = ss.stop;
+        __syncwarp();
+        if (stop_now) break;
     }
     if (lane == 0)
     {

@@ -1582,11 +1582,17 @@ static int wait_cloud(Workspace* ws, const b200icp_cloud* c)
     return B200ICP_OK;
 }
 
-// Switches (environment, read once): the search stage is the per-lane shell walk
-// (tile_search.cuh); B200ICP_SEARCH=item selects the item sweep (item_sweep.cuh)
-// and B200ICP_SEARCH=sweep the radius-wide tile sweep (sweep_search.cuh) instead --
-// same results, measured slower on LiDAR scans, kept for A/B runs;
-// B200ICP_WPI=1|2|4 the warps that share one item in the tile sweep.
+// Switches (environment, read once).  The search stage is chosen per launch: the
+// per-lane shell walk (tile_search.cuh) for single registrations and queries -- one
+// wave of items, the kernel lasts as long as its slowest item, and the walk's items
+// are the shortest -- and the item sweep (item_sweep.cuh) when kBatchJobs or more
+// jobs share a launch (Monte-Carlo loop, loop-closure candidates): many waves, so
+// throughput counts, and the sweep executes fewer, converged instructions
+// (measured: C4 4263 against 2359 registrations/s).
+// B200ICP_SEARCH=walk|item forces one of them, B200ICP_SEARCH=sweep selects the
+// radius-wide tile sweep (sweep_search.cuh); all give the same results.
+// B200ICP_WPI=1|2|4: the warps that share one item in the tile sweep.
+constexpr size_t kBatchJobs = 8;  // jobs per launch from which the item sweep is the search stage
 struct SearchConfig
 {
     bool sweep = false;
@@ -1594,13 +1600,14 @@ struct SearchConfig
     bool graphs = true;  // B200ICP_GRAPH=0: no CUDA-graph replay of single registrations
     bool tma = false;    // B200ICP_TMA=1 (with B200ICP_SEARCH=item): runs staged with cp.async.bulk + mbarriers
     bool seeds = true;   // B200ICP_SEED=0: searches never take their bound from the previous neighbour rows
-    bool walk = true;    // the per-lane shell walk (tile_search.cuh); B200ICP_SEARCH=item: the item sweep (item_sweep.cuh)
+    bool walk = false;   // B200ICP_SEARCH=walk: always the per-lane shell walk
+    bool item = false;   // B200ICP_SEARCH=item: always the item sweep
 };
 static const SearchConfig& search_config()
 {
     static const SearchConfig cfg = [] {
         SearchConfig c;
-        if (const char* s = getenv("B200ICP_SEARCH")) c.sweep = (strcmp(s, "sweep") == 0), c.walk = (strcmp(s, "item") != 0) && !c.sweep;
+        if (const char* s = getenv("B200ICP_SEARCH")) c.sweep = (strcmp(s, "sweep") == 0), c.walk = (strcmp(s, "walk") == 0), c.item = (strcmp(s, "item") == 0);
         if (const char* w = getenv("B200ICP_WPI")) c.wpi = atoi(w);
         if (const char* g = getenv("B200ICP_GRAPH")) c.graphs = atoi(g) != 0;
         if (const char* g = getenv("B200ICP_SEED")) c.seeds = atoi(g) != 0;
@@ -1640,7 +1647,8 @@ static void launch_search_k(const ::b200icp* ctx, Workspace* ws, size_t max_poin
     cudaStream_t        s = ws->stream;
     const SearchConfig& cfg = search_config();
     const size_t        items = std::max<size_t>(1, (max_points + kItem - 1) / kItem);
-    if (!cfg.sweep && !cfg.walk)
+    const bool use_item = cfg.item || (!cfg.walk && !cfg.sweep && njobs >= kBatchJobs);
+    if (use_item)
     {
         // resident CTAs on one SM (registers and the opted-in dynamic shared memory); every instantiation opts in once
         static int  resident = 0;
@@ -1666,7 +1674,7 @@ static void launch_search_k(const ::b200icp* ctx, Workspace* ws, size_t max_poin
         kern<<<dim3(G, (unsigned)njobs), kChunk, sizeof(ItemSmem), s>>>(d_clouds, d_jobs, D, cap_d2, gate, seed_nn,
                                                                        seed_k, cfg.tma ? 1 : 0, epi);
     }
-    else if (cfg.walk)
+    else if (!cfg.sweep)
     {
         // resident CTAs of the walk on one SM (registers and shared memory)
         static int resident = 0;

@@ -1,7 +1,8 @@
-"""The alternative search stages -- the radius-wide tile sweep (sweep_search.cuh, B200ICP_SEARCH=sweep), the item
-sweep (item_sweep.cuh, B200ICP_SEARCH=item) and its cp.async.bulk + mbarrier staging (B200ICP_TMA=1); the switches are
-read once per process -- must give the same bits as the default per-lane walk: the kNN / matcher / registration
-parity tests are re-run in a child process with the switch set."""
+"""The search stages -- the per-lane walk (tile_search.cuh), the item sweep (item_sweep.cuh) with and without its
+cp.async.bulk + mbarrier staging (B200ICP_TMA=1), the radius-wide tile sweep (sweep_search.cuh) -- must give the same
+bits.  By default the library picks the walk for single jobs and the item sweep for batched launches; the kNN /
+matcher / registration / batch parity tests are re-run in a child process with each stage FORCED for every launch
+(B200ICP_SEARCH, read once per process)."""
 import os
 import subprocess
 import sys
@@ -23,6 +24,12 @@ def _run(extra_env, files):
 @pytest.mark.timeout(900)
 def test_parity_suite_with_tile_sweep_search():
     _run({"B200ICP_SEARCH": "sweep"},
+         ["tests/test_gpu_knn.py", "tests/test_gpu_match.py", "tests/test_gpu_align.py", "tests/test_gpu_multi.py"])
+
+
+@pytest.mark.timeout(900)
+def test_parity_suite_with_walk_forced():
+    _run({"B200ICP_SEARCH": "walk"},
          ["tests/test_gpu_knn.py", "tests/test_gpu_match.py", "tests/test_gpu_align.py", "tests/test_gpu_multi.py"])
 
 

@@ -81,14 +81,24 @@ extern "C" int b200icp_create(const b200icp_params_t* params, int device, b200ic
     ctx->sm_count = prop.multiProcessorCount;
     make_dev_params(ctx->P, ctx->D);
     memset(&ctx->prof, 0, sizeof(ctx->prof));
-    // first workspace now, so that a broken device fails here
-    Workspace* ws = ctx->acquire();
-    if (!ws)
+    // the first workspaces now: a broken device fails here, and the threads that later call into this object
+    // at the same time (the reference's pools: one per-scan thread + hw/2 threads for nearby key-frames,
+    // LidarOdometry.cpp:94-96) find a stream, events and pinned staging ready instead of creating them -- with
+    // device-wide synchronisations -- in the middle of someone else's registration
+    Workspace* first[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (auto& w : first)
+    {
+        w = ctx->acquire();
+        if (!w) break;
+    }
+    if (!first[0])
     {
         delete ctx;
         return B200ICP_ERR_CUDA;
     }
-    ctx->release(ws);
+    if (Workspace* up = ctx->acquire(true)) ctx->release(up);  // and one for uploads / index builds
+    for (auto* w : first)
+        if (w) ctx->release(w);
     *out = ctx;
     return B200ICP_OK;
 }

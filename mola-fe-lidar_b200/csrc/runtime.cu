@@ -32,6 +32,9 @@ int Workspace::init(int dev)
     for (auto& e : ev) B2_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     B2_CUDA_TRY(cudaMalloc(&d_flag, 256));
     B2_CUDA_TRY(cudaMallocHost(&h_flag, 256));
+    // pinned staging sized once for what a call moves (job records, results, counters): growing it later is a
+    // cudaFreeHost + cudaMallocHost, both device-wide synchronisations
+    if (int r = reserve_pinned((size_t)256 << 10)) return r;
     return B200ICP_OK;
 }
 
@@ -55,12 +58,14 @@ void Workspace::destroy()
 int Workspace::reserve_device(size_t bytes)
 {
     if (bytes <= d_bytes) return B200ICP_OK;
-    B2_CUDA_TRY(cudaStreamSynchronize(stream));
+    // Growth is STREAM-ORDERED (the device's pool is kept warm, capi.cu): cudaFree / cudaMalloc would wait for every
+    // stream of the device -- the registrations other threads are running -- each time a workspace meets its first
+    // large cloud.  Work already enqueued on this stream keeps the old block until it has run.
     drop_align_graphs();  // they hold pointers into the old allocation
-    if (d_scratch) B2_CUDA_TRY(cudaFree(d_scratch));
+    if (d_scratch) B2_CUDA_TRY(cudaFreeAsync(d_scratch, stream));
     d_scratch = nullptr, d_bytes = 0;
     const size_t want = align_up(bytes + bytes / 4, 1 << 20);
-    B2_CUDA_TRY(cudaMalloc(&d_scratch, want));
+    B2_CUDA_TRY(cudaMallocAsync(&d_scratch, want, stream));
     d_bytes = want;
     return B200ICP_OK;
 }

@@ -61,7 +61,10 @@ __device__ unsigned long long g_dbg_phase[16];
 
 constexpr int kSwRanges = 224;   // runs of sorted points per pass
 constexpr int kSwBlocks = 384;   // blocks the box of a pass may touch
-constexpr int kSwStage = 256;    // staged points per evaluation chunk
+#ifndef B200ICP_SW_STAGE
+#define B200ICP_SW_STAGE 256
+#endif
+constexpr int kSwStage = B200ICP_SW_STAGE;  // staged points per evaluation chunk (>= 160; the TMA variant halves it)
 constexpr int kSwList = 16;      // keys a lane may collect between two folds
 constexpr int kSwBudget = 2048;  // points one pass may load
 

@@ -47,3 +47,36 @@ meta.update(pose=[float(v) for v in r["pose"]], n_iterations=int(r["n_iterations
             n_pairings=int(r["n_pairings"]), quality=float(r["quality"]), truth=[float(v) for v in pose])
 json.dump(meta, open(os.path.join(HERE, "icp_c1.json"), "w"), indent=1)
 print("golden written:", len(sel), "knn queries;", meta)
+
+# edges_planes_c1.npz : FilterEdgesPlanes classes of a 20,000-point sub-scan from an INDEPENDENT evaluation (numpy
+#             eigvalsh / eigh on the per-voxel covariance in float64, voxels found with np.unique), kept only where
+#             every gate is away from its threshold by more than 2 % (so that the Jacobi solver of the oracle / the
+#             device and LAPACK must agree): per voxel the class (0 none, 1 edges, 2 planes), per point the voxel.
+A = scene.make_pair_c1(seed=5, n=20000, sigma=0.01)[0]
+res, mx20, mx10, mn20, mn10, minpts = np.float32(1.0), 30.0, 30.0, 80.0, 80.0, 5
+vox = np.floor(A / res).astype(np.int64)
+uniq, inv, cnt = np.unique(vox, axis=0, return_inverse=True, return_counts=True)
+inv = inv.reshape(-1)
+cls = np.zeros(len(uniq), dtype=np.int8)
+sure = np.zeros(len(uniq), dtype=bool)
+for v in range(len(uniq)):
+    if cnt[v] < minpts:
+        sure[v] = True
+        continue
+    P = A[inv == v].astype(np.float64)
+    C = np.cov(P.T, bias=True)
+    w, V = np.linalg.eigh(C)
+    e0, e1, e2 = w
+    if e0 <= 0:
+        continue  # degenerate: leave it to the parity tests
+    m = 0.02
+    is_edge = e2 < mx20 * e0 and e1 < mx10 * e0
+    is_plane = (not is_edge) and e2 > mn20 * e0 and e1 > mn10 * e0 and abs(V[2, 0]) < 0.9
+    margins = [abs(e2 / (mx20 * e0) - 1), abs(e1 / (mx10 * e0) - 1), abs(e2 / (mn20 * e0) - 1), abs(e1 / (mn10 * e0) - 1),
+               abs(abs(V[2, 0]) / 0.9 - 1)]
+    sure[v] = min(margins) > m
+    cls[v] = 1 if is_edge else (2 if is_plane else 0)
+np.savez_compressed(os.path.join(HERE, "edges_planes_c1.npz"), pts=A, voxel_of_point=inv.astype(np.int32),
+                    voxel_class=cls, voxel_sure=sure)
+print("golden written: edges/planes,", int(sure.sum()), "of", len(uniq), "voxels unambiguous;",
+      int((cls[sure] == 1).sum()), "edges,", int((cls[sure] == 2).sum()), "planes")

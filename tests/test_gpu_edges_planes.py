@@ -93,3 +93,18 @@ def test_module_registers_the_configured_layer(oracle):
     with pytest.raises(Exception, match="b200_register_layer"):
         lidar_odometry.LidarOdometry(yaml_text=lidar_odometry.system_yaml(
             extra=extra.replace("full_decim", "corners")))
+
+
+def test_matches_independent_golden(icp):
+    """The device against tests/golden/edges_planes_c1.npz (numpy eigh on np.unique voxels, unambiguous voxels only)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "edges_planes_c1.npz"))
+    cloud = icp.upload_raw(np.ascontiguousarray(g["pts"]))
+    layers, f, _ = icp.filter_edges_planes(cloud, voxel_filter_decimation=1, full_pointcloud_decimation=1)
+    cls_of_point = np.where(f & 1, 1, np.where(f & 2, 2, 0))
+    want = g["voxel_class"][g["voxel_of_point"]]
+    sure = g["voxel_sure"][g["voxel_of_point"]]
+    assert np.array_equal(cls_of_point[sure], want[sure])
+    for c in layers:
+        c.free()
+    cloud.free()

@@ -246,3 +246,17 @@ def test_filter_edges_planes_known_answers(oracle, rng):
     assert np.array_equal(np.flatnonzero(f & 4), np.arange(0, 200, 7))
     f, nv = one(np.array([[np.nan, 0, 0], [0.5, 0.5, 0.5]]))
     assert f[0] == 0 and f[1] == 4
+
+
+def test_filter_edges_planes_matches_independent_golden(oracle):
+    """tests/golden/edges_planes_c1.npz: the voxel classes from numpy's eigh on np.unique voxels, kept where every gate
+    is at least 2 % away from its threshold (make_golden.py) -- the oracle's hash/sort + Jacobi path must agree."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "edges_planes_c1.npz"))
+    f, _ = oracle.filter_edges_planes(g["pts"], voxel_filter_decimation=1, full_pointcloud_decimation=1)
+    cls_of_point = np.where(f & 1, 1, np.where(f & 2, 2, 0))
+    want = g["voxel_class"][g["voxel_of_point"]]
+    sure = g["voxel_sure"][g["voxel_of_point"]]
+    assert sure.sum() > 3000 and (want[sure] == 1).any() and (want[sure] == 2).any()
+    assert np.array_equal(cls_of_point[sure], want[sure])
+    assert (f & 4).all()

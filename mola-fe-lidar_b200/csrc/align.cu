@@ -1130,7 +1130,51 @@ __device__ int finish_outer_iteration(JobDev& J, const Pose& Tn, uint32_t npair,
         atomicSub(n_active, 1u);
         return 0;
     }
-    if (!same_as_two_back) return 0;
+    if (!same_as_two_back)
+    {
+        // Longer cycles (period 3 .. kCycleMax; a 3-cycle between three pairing sets is as common on coarse clouds
+        // as the 2-cycle).  Same recognition -- the new pose and pairing count equal those of `p` iterations before,
+        // p times in a row -- but a simpler jump: whole periods are skipped (the state after them is this one) and
+        // the remaining (left mod p) iterations simply run; the loop then ends with MaxIterations by itself.
+        if (allow_cycle && P.detect_cycles && J.cycle_at == 0 && P.run_from_iteration == 0 && P.run_up_to_iteration == 0)
+        {
+            const double tol = (P.detect_cycles >= 2) ? 1e-11 : 0.0;
+            uint32_t     found = 0;
+            for (uint32_t p = 3; p <= (uint32_t)kCycleMax; p++)
+            {
+                bool same = it > p && J.hist_npair[(it - p) % kCycleMax] == npair;
+                if (same)
+                {
+                    const double* h = J.hist_pose[(it - p) % kCycleMax];
+                    for (int i = 0; i < 9; i++) same = same && (fabs(Tn.R[i] - h[i]) <= tol);
+                    for (int i = 0; i < 3; i++) same = same && (fabs(Tn.t[i] - h[9 + i]) <= tol);
+                }
+                J.cyc_hits[p] = same ? J.cyc_hits[p] + 1 : 0;
+                if (!found && J.cyc_hits[p] >= p) found = p;
+            }
+            double* h = J.hist_pose[it % kCycleMax];
+            for (int i = 0; i < 9; i++) h[i] = Tn.R[i];
+            for (int i = 0; i < 3; i++) h[9 + i] = Tn.t[i];
+            J.hist_npair[it % kCycleMax] = npair;
+            J.hist_inner[it % kCycleMax] = inner;
+            if (found)
+            {
+                const uint32_t left = P.max_iterations - it, periods = left / found;
+                uint32_t       inner_per_period = 0;
+                for (uint32_t k = 0; k < found; k++) inner_per_period += J.hist_inner[(it - k) % kCycleMax];
+                J.cycle_at = it;
+                J.iter = it + periods * found;
+                J.inner_iters_total += periods * inner_per_period;
+                if (J.iter >= P.max_iterations)
+                {   // a whole number of periods was left: this state is the final one
+                    J.status = 1;
+                    J.term_reason = B200ICP_TERM_MAX_ITERATIONS;
+                    atomicSub(n_active, 1u);
+                }
+            }
+        }
+        return 0;
+    }
     // period 2 from here on: `left` more iterations would run; an even number leaves this state, an odd number
     // the one of the previous iteration (pose_i, moments and pairings of iteration i - 1)
     const uint32_t left = P.max_iterations - it;
@@ -2094,7 +2138,9 @@ static int run_wave(::b200icp* ctx, Workspace* ws, const IcpDevParams& D, size_t
                                        D.max_iterations);
         max_runs = std::max(max_runs, runs);
     }
-    if (n == 1) ctx->expected_runs.store((int)max_runs);
+    // the next registration's first batch is sized from this one -- unless this one ended in a recognised cycle: an
+    // outlier that says nothing about the next scan pair
+    if (n == 1 && h_jobs[0].cycle_at == 0) ctx->expected_runs.store((int)max_runs);
     if (getenv("B200ICP_DBG_TAIL"))
         fprintf(stderr, "[dbg tail] job 0: final moment sum %u cycles, GN loop %u cycles (%u inner), end of iteration %u "
                         "cycles; %u outer iterations, %u inner in total\n",

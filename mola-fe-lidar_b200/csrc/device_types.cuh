@@ -41,6 +41,7 @@ constexpr int kItem = 32;      // queries per work item = one warp round
 constexpr int kNumMoments = 192; // three 8x8 tiles of the 16x16 moment matrix S (align.cu)
 constexpr int kMicroBits = 3;   // octant of the point inside its fine cell: low bits of the sort key
 constexpr int kGroup = 8;       // sorted points per bounding-box group
+constexpr int kCycleMax = 6;    // longest period of a pose cycle the iteration loop recognises
 constexpr int kSortBits = 30 + 6 + kMicroBits + 1;  // Morton30 | fine6 | octant3, +1 for the invalid key
 
 struct GridDev
@@ -99,6 +100,12 @@ struct JobDev
     uint32_t inner_prev;
     uint32_t cycle_hits;   // consecutive iterations whose pose repeated the pose of two iterations before
     uint32_t cycle_at;     // outer iteration at which a period-2 cycle was recognised (0: none)
+    // longer cycles (period 3 .. kCycleMax, align.cu): the poses, pairing counts and inner iterations of the last
+    // kCycleMax outer iterations (slot = iteration % kCycleMax) and, per period, how many consecutive iterations
+    // repeated the iteration `period` back
+    double   hist_pose[kCycleMax][12];
+    uint32_t hist_npair[kCycleMax], hist_inner[kCycleMax];
+    uint32_t cyc_hits[kCycleMax + 1];
     uint32_t dbg_tail[4];  // development probe (last outer iteration): cycles of the final moment sum, of the
                            // Gauss-Newton loop, of the end-of-iteration step; inner iterations
 };

@@ -136,11 +136,12 @@ def test_varying_cloud_sizes_back_to_back(icp, oracle):
 
 
 def test_period_two_fast_forward_matches_the_full_loop(capi, oracle):
-    """Registrations of coarse clouds that end in a 2-cycle between two pairing sets run to maxIterations in the
-    reference.  The device recognises the cycle (pose and pairing count repeating those of two iterations before,
-    twice in a row) and jumps to the end state: same iteration count, termination reason, pairing count and
-    quality as running the loop out (B200ICP_CYCLE=0 in a child process), poses within 1e-10 -- and equal to the
-    oracle's within the stated tolerance."""
+    """Registrations of coarse clouds that end in a cycle between two or three pairing sets run to maxIterations in
+    the reference (in this sequence: one 3-cycle, pair 3 -> 4, and one 2-cycle, pair 11 -> 12).  The device recognises
+    the cycle (pose and pairing count repeating those of p iterations before, p times in a row, p = 2 .. 6) and jumps
+    to the end state: same iteration count, termination reason, pairing count and quality as running the loop out
+    (B200ICP_CYCLE=0 in a child process), poses within 1e-10 -- and equal to the oracle's within the stated
+    tolerance."""
     import json
     import os
     import subprocess
@@ -179,7 +180,7 @@ print(json.dumps(out))
     assert runs["1"] == runs["0"]  # bitwise-only recognition never changes a bit
     runs["1"] = runs["2"]
     # the sequence must actually contain registrations that exhaust the iteration budget
-    assert any(r["term"] == 3 and r["it"] == 100 for r in runs["1"])
+    assert sum(r["term"] == 3 and r["it"] == 100 for r in runs["1"]) >= 2
     # and the oracle agrees on one of them
     scans, _ = scene.make_sequence(13, seed=1)
     k = next(i for i, r in enumerate(runs["1"]) if r["term"] == 3)

@@ -57,14 +57,15 @@ extern "C" int b200icp_create(const b200icp_params_t* params, int device, b200ic
         // Give the pool a reserve once per device: growing it later (keyframe
         // clouds stay alive in the world model, LidarOdometry.cpp:384-388) maps
         // fresh memory inside cudaMallocAsync, a multi-millisecond stall on the
-        // per-scan path.  1 GiB of 180; returned to the pool at once.
+        // per-scan path.  4 GiB of 180 (clouds of the key-frames, plus the scratch of every workspace, which also
+        // comes from the pool); returned to the pool at once.
         static std::mutex       pm;
         static std::vector<int> primed;
         std::lock_guard<std::mutex> lk(pm);
         if (std::find(primed.begin(), primed.end(), device) == primed.end())
         {
             void* p = nullptr;
-            if (cudaMallocAsync(&p, (size_t)1 << 30, 0) == cudaSuccess)
+            if (cudaMallocAsync(&p, (size_t)4 << 30, 0) == cudaSuccess)
             {
                 cudaFreeAsync(p, 0);
                 cudaStreamSynchronize(0);

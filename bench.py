@@ -696,11 +696,12 @@ def run_b200(args, rank, world, local_rank):
     # reference arm count; `e2e_full_module` below runs the module as shipped.
     replays = {"n": 0}
 
-    def run_module(extra_yaml, steps, warm, voxel=None, feed="async"):
+    def run_module(extra_yaml, steps, warm, voxel=None, feed="async", passes=1):
         """feed "async": scans go in through onNewObservation as the reference's data source delivers them
         (LidarOdometry.cpp:162-187: enqueue on the 1-thread pool), as fast as the module takes them (at most 4
         waiting, so the >10-queued drop rule never fires); "sync": each scan is processed on the calling thread
-        before the next one is handed over."""
+        before the next one is handed over.  passes > 1: that many timed windows of `steps` scans one after the
+        other on the same module; the MEDIAN window is returned, all of them are kept in run_module.windows."""
         # additive key b200_device: this rank's GPU
         lo = lidar_odometry.LidarOdometry(
             yaml_text=lidar_odometry.system_yaml(voxel_resolution=voxel,
@@ -718,17 +719,23 @@ def run_b200(args, rank, world, local_rank):
             hand_over(s, stamp)
             stamp += 0.1
         lo.wait_idle()
-        st0 = lo.state()
-        barrier()
-        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e2.record()
-        for s in range(warm + 1, warm + 1 + steps):
-            hand_over(s, stamp)
-            stamp += 0.1
-        lo.wait_idle()  # every queued scan and extra-edge registration belongs to the timed region
-        e3.record()
-        barrier()
-        ms = e2.elapsed_time(e3)
+        windows = []
+        nxt = warm + 1
+        for _ in range(passes):
+            st0 = lo.state()
+            barrier()
+            e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e2.record()
+            for s in range(nxt, nxt + steps):
+                hand_over(s, stamp)
+                stamp += 0.1
+            lo.wait_idle()  # every queued scan and extra-edge registration belongs to the timed region
+            e3.record()
+            barrier()
+            nxt += steps
+            st = lo.state()
+            windows.append((e2.elapsed_time(e3), int(st["n_icp"] - st0["n_icp"]),
+                            int(st["n_processed"] - st0["n_processed"])))
         st = lo.state()
         prof_mod = lo.profile()
         replays["n"] = sum(capi.ICP.profile_of_handle(lo.icp_handle(kind))["graph_replays"] for kind in (0, 1, 2))
@@ -737,10 +744,16 @@ def run_b200(args, rank, world, local_rank):
         sections = {k.replace("doProcessNewObservation.", ""): [round(v[1] / max(v[0], 1) * 1e3, 3), round(v[2] * 1e3, 3)]
                     for k, v in prof_mod.items() if v[0] > 0 and not k.startswith("exception") and v[1] > 1e-5}
         log(f"[bench] module sections, [mean, max] ms per call over {n_all} scans:", json.dumps(sections))
-        return ms, int(st["n_icp"] - st0["n_icp"]), int(st["n_processed"] - st0["n_processed"]), \
-            int(st["n_keyframes"])
+        run_module.windows = [w[0] for w in windows]
+        ms, regs, scans_done = sorted(windows)[len(windows) // 2]
+        return ms, regs, scans_done, int(st["n_keyframes"])
 
-    ms_e2e, e2e_regs, e2e_scans, _ = run_module("  b200_extra_edge_checks: false\n", args.steps, args.warmup)
+    # the headline leg: the same K scans three times, each time through a fresh module, the median run reported (a
+    # rare stall of some tens of milliseconds -- all the module's threads at once -- otherwise decides a
+    # 20-millisecond timed region)
+    e2e_runs = sorted(run_module("  b200_extra_edge_checks: false\n", args.steps, args.warmup) for _ in range(3))
+    e2e_windows_ms = [r[0] for r in e2e_runs]
+    ms_e2e, e2e_regs, e2e_scans, _ = e2e_runs[1]
     e2e_graph_replays = int(replays["n"])
     ms_sync, sync_regs, _, _ = run_module("  b200_extra_edge_checks: false\n", args.steps, args.warmup, feed="sync")
     ms_full, full_regs, full_scans, full_kfs = run_module("", args.steps, max(args.warmup, 12))
@@ -817,6 +830,8 @@ def run_b200(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": n_pts * 12,
                     "d2h_bytes_per_step": 1128, "ms_per_step": ms_e2e_max / max(float(u[1]) / world, 1.0),
                     "cuda_graph_replays_rank0": e2e_graph_replays,
+                    "windows_ms_rank0": [round(w, 3) for w in e2e_windows_ms],
+                    "windows_note": "the same K scans three times, each through a fresh module; value = the median run",
                     "api": "LidarOdometry.onNewObservation (b200lo_enqueue_observation: the reference's asynchronous "
                            "entry, LidarOdometry.cpp:162-187), pinned host SoA, at most 4 scans waiting; "
                            "b200_extra_edge_checks: false (one consecutive-scan registration per scan); the module "

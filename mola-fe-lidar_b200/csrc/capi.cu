@@ -1,6 +1,7 @@
 // capi.cu -- extern "C" entry points declared in include/b200icp.h.
 #include <cmath>
 #include <algorithm>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -86,20 +87,23 @@ extern "C" int b200icp_create(const b200icp_params_t* params, int device, b200ic
     // at the same time (the reference's pools: one per-scan thread + hw/2 threads for nearby key-frames,
     // LidarOdometry.cpp:94-96) find a stream, events and pinned staging ready instead of creating them -- with
     // device-wide synchronisations -- in the middle of someone else's registration
-    Workspace* first[4] = {nullptr, nullptr, nullptr, nullptr};
-    for (auto& w : first)
+    // (as many as that pool can have threads: hardware_concurrency / 2 + the per-scan thread + one spare)
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t   n_first = std::min<size_t>(16, std::max<size_t>(4, hw / 2 + 2));
+    std::vector<Workspace*> first;
+    for (size_t i = 0; i < n_first; i++)
     {
-        w = ctx->acquire();
+        Workspace* w = ctx->acquire();
         if (!w) break;
+        first.push_back(w);
     }
-    if (!first[0])
+    if (first.empty())
     {
         delete ctx;
         return B200ICP_ERR_CUDA;
     }
     if (Workspace* up = ctx->acquire(true)) ctx->release(up);  // and one for uploads / index builds
-    for (auto* w : first)
-        if (w) ctx->release(w);
+    for (auto* w : first) ctx->release(w);
     *out = ctx;
     return B200ICP_OK;
 }

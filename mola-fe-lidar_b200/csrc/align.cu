@@ -510,10 +510,59 @@ __global__ void __launch_bounds__(kChunk, B200ICP_ITEM_MINB)
 // Warps draw items from the job's counter (dynamic: the results do not depend
 // on who searches what, and items differ a lot in cost).  Per item (<= 32
 // queries, one per lane): box of the queries' home cells -> tile -> search.
+// Quality pass (k = 1, radius = the evaluator's threshold) right after a matcher search: most queries need no
+// search at all.  A lane's seeds are the <= k nearest points the matcher found at the pose `cert_Rt`; here the
+// question is only whether ANY point lies within the radius at the current pose.
+//   * a seed within the radius  -> yes, and that seed is a real point: the search could only find it or a closer one;
+//   * no seed within the radius -> every other point was at least `reach` away from the query at cert_Rt (the
+//     farthest seed if the list is full; the matcher's own radius if it is not: then the list holds ALL points inside
+//     it), and the query has moved by `mv` since: if reach - mv still exceeds the radius (2 mm of slack for the
+//     float32 arithmetic of both distance evaluations), the answer is no.
+// Lanes that are settled either way skip the search; the others search as usual.  An item whose lanes are all
+// settled costs two loads per lane instead of a tile build and a walk.
+// Returns 0: not settled, 1: a point within the radius (hit_key), 2: none.
+template <int K>
+__device__ __forceinline__ int settle_quality(const CloudView& cvG, const uint32_t* __restrict__ row, uint32_t sk,
+                                               const double* cert_Rt, const float4& pl, float qx, float qy, float qz,
+                                               float radius_d2, float rows_cap_d2, uint64_t& hit_key)
+{
+    double rx_, ry_, rz_;
+    transform_point(cert_Rt, pl, rx_, ry_, rz_);
+    const float rx = (float)rx_, ry = (float)ry_, rz = (float)rz_;
+    if (!((fabsf(rx) <= FLT_MAX) && (fabsf(ry) <= FLT_MAX) && (fabsf(rz) <= FLT_MAX))) return 0;
+    float    best = INFINITY, far = 0.0f;
+    uint32_t best_idx = 0;
+    bool     full = true;
+#pragma unroll
+    for (int i = 0; i < B200ICP_MAX_KNN; i++)
+        if ((uint32_t)i < sk)
+        {
+            const uint32_t p = row[i];
+            if (p == kInvalid)
+            {
+                full = false;
+                continue;
+            }
+            const float4 c = __ldg(cvG.pts + p);
+            const float  d = dist2(qx, qy, qz, c), dr = dist2(rx, ry, rz, c);
+            if (d < best) best = d, best_idx = __float_as_uint(c.w);
+            far = fmaxf(far, dr);
+        }
+    if (best < radius_d2)
+    {
+        hit_key = make_key(best, best_idx);
+        return 1;
+    }
+    const float mv = sqrtf(dist2(qx, qy, qz, make_float4(rx, ry, rz, 0.f)));
+    const float reach = full ? sqrtf(far) : sqrtf(rows_cap_d2);
+    return (reach - mv - 2e-3f > sqrtf(radius_d2) * 1.001f) ? 2 : 0;
+}
+
 template <int K, class F>
 __device__ __forceinline__ void for_each_item(WarpTile& W, const CloudView& cvL, const CloudView& cvG,
                                               const GridDev& grid, const double* Rt, uint32_t n_items,
-                                              uint32_t* next_item, float cap_d2, const SeedRows& seed, F&& f)
+                                              uint32_t* next_item, float cap_d2, const SeedRows& seed,
+                                              const double* cert_Rt, float rows_cap_d2, F&& f)
 {
     const int lane = threadIdx.x & 31;
     for (;;)
@@ -532,17 +581,24 @@ __device__ __forceinline__ void for_each_item(WarpTile& W, const CloudView& cvL,
         transform_point(Rt, pl, gx, gy, gz);
         const float qx = (float)gx, qy = (float)gy, qz = (float)gz;
         const bool  finite = has && (fabsf(qx) <= FLT_MAX) && (fabsf(qy) <= FLT_MAX) && (fabsf(qz) <= FLT_MAX);
+        // quality pass: settled without a search?
+        int      settle = 0;
+        uint64_t hit_key = 0;
+        if (K == 1 && cert_Rt && seed.rows && finite)
+            settle = settle_quality<K>(cvG, seed.rows + (size_t)(first + lane) * seed.k, seed.k, cert_Rt, pl, qx, qy, qz,
+                                        cap_d2, rows_cap_d2, hit_key);
+        const bool settled = settle != 0;
         // this lane's radius cap: the caller's, or the tighter bound of its seeds
         float cap = cap_d2;
-        if (seed.rows && finite)
+        if (seed.rows && finite && !settled)
             cap = seeded_cap<K>(cvG, seed.rows + (size_t)(first + lane) * seed.k, seed.k, qx, qy, qz, cap_d2);
         // shells the widest lane of the item may need (warp-uniform)
-        float capmax = finite ? cap : 0.0f;
+        float capmax = (finite && !settled) ? cap : 0.0f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) capmax = fmaxf(capmax, __shfl_xor_sync(0xFFFFFFFFu, capmax, o));
         const int       S = search_shells(grid, capmax);
         const QueryCell qc = locate_query(grid, S, qx, qy, qz);
-        const bool      hasq = has && qc.valid;
+        const bool      hasq = has && qc.valid && !settled;
         int lo[3] = {hasq ? qc.hx : INT_MAX, hasq ? qc.hy : INT_MAX, hasq ? qc.hz : INT_MAX};
         int hi[3] = {hasq ? qc.hx : INT_MIN, hasq ? qc.hy : INT_MIN, hasq ? qc.hz : INT_MIN};
 #pragma unroll
@@ -557,6 +613,7 @@ __device__ __forceinline__ void for_each_item(WarpTile& W, const CloudView& cvL,
         uint64_t       key[K];
 #pragma unroll
         for (int i = 0; i < K; i++) key[i] = sent;
+        if (settle == 1) key[0] = hit_key;  // a real point within the radius
         if (hasq)
         {
             if (tiled)
@@ -585,6 +642,7 @@ struct SearchSmem
     WarpTile tile[kChunk / 32];
     GridDev  grid;
     double   Rt[12];
+    double   Rt_rows[12];  // pose of the matcher search whose rows seed this one (quality pass)
     uint32_t n_items;
 };
 
@@ -609,11 +667,14 @@ __global__ void __launch_bounds__(kChunk, B200ICP_SEARCH_MINB)
     if (tid < 12) sm.Rt[tid] = (tid < 9) ? J.R[tid] : J.t[tid - 9];
     if (tid == 12) sm.grid = *cvG.grid;
     if (tid == 13) sm.n_items = cvL.grid->n_items;
+    if (tid >= 32 && tid < 44) sm.Rt_rows[tid - 32] = J.rows_Rt[tid - 32];
     __syncthreads();
     const uint32_t n_items = (sm.grid.n_valid > 0) ? sm.n_items : 0u;
     SeedRows       seed = {nullptr, seed_k};
     if (seed_nn && J.rows_valid) seed.rows = seed_nn + (size_t)J.pair_base * seed_k;
-    for_each_item<K>(sm.tile[tid >> 5], cvL, cvG, sm.grid, sm.Rt, n_items, &J.next_item, cap_d2, seed,
+    // the quality pass after a matcher run of this registration: settle_quality
+    const double* cert = (gate == 2 && K == 1 && seed.rows && J.rows_pose_valid) ? sm.Rt_rows : nullptr;
+    for_each_item<K>(sm.tile[tid >> 5], cvL, cvG, sm.grid, sm.Rt, n_items, &J.next_item, cap_d2, seed, cert, P.thr2,
                      [&](bool has, uint32_t pos, uint32_t orig, uint64_t (&key)[K], uint64_t sent) {
                          epi(J, cvG, has, pos, orig, key, sent);
                      });
@@ -1201,7 +1262,13 @@ __device__ void solve_job_warp(JobDev& J, SolveSmem& ss, const IcpDevParams& P, 
     if (lane == 0)
     {
         J.next_item = 0;                                   // the next search draws items from 0 again
-        if (matcher_active(P, J.iter)) J.rows_valid = 1;   // this iteration's search wrote the neighbour rows
+        if (matcher_active(P, J.iter))
+        {   // this iteration's search wrote the neighbour rows, at the pose the job still holds
+            J.rows_valid = 1;
+            J.rows_pose_valid = 1;
+            for (int i = 0; i < 9; i++) J.rows_Rt[i] = J.R[i];
+            for (int i = 0; i < 3; i++) J.rows_Rt[9 + i] = J.t[i];
+        }
     }
     const bool     p2p = (P.matcher_kind == B200ICP_MATCHER_POINTS_DISTANCE);
     const uint32_t npair = (uint32_t)(pairing_count(ss.S, p2p) + 0.5);
@@ -1458,7 +1525,8 @@ __global__ void __launch_bounds__(kHornSolveThreads)
     JobDev&        J = jobs[job];
     if (threadIdx.x == 0) J.next_item = 0;  // the next search draws items from 0 again
     if (J.status != 0) return;
-    if (threadIdx.x == 0 && matcher_active(P, J.iter)) J.rows_valid = 1;  // this iteration's search wrote them
+    if (threadIdx.x == 0 && matcher_active(P, J.iter))
+        J.rows_valid = 1, J.rows_pose_valid = 0;  // this iteration's search wrote them (pose not recorded on this path)
     const int tid = threadIdx.x;
     __shared__ double sH[kHornVals];
     // the matcher's moments (needed for the covariance at the end) are already in J.M: the fit kernel's tail

@@ -93,6 +93,8 @@ struct JobDev
     uint32_t next_item;    // work counter of the search stage (reset by the solver)
     uint32_t evaluated;    // quality + covariance taken (once, after the job finished)
     uint32_t rows_valid;   // the job's neighbour rows hold a matcher search of this registration (seeds)
+    uint32_t rows_pose_valid;  // ... and rows_Rt is the pose that search ran at (quality certificate, align.cu)
+    double   rows_Rt[12];
     uint32_t chunk_base;   // first chunk partial / first group partial + ticket of this job in the launch's
     uint32_t group_base;   //   fit buffers (align.cu, "chunk partials")
     uint32_t groups_done;  // arrival counter of the job's group reductions; zero between launches

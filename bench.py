@@ -696,12 +696,11 @@ def run_b200(args, rank, world, local_rank):
     # reference arm count; `e2e_full_module` below runs the module as shipped.
     replays = {"n": 0}
 
-    def run_module(extra_yaml, steps, warm, voxel=None, feed="async", passes=1):
+    def run_module(extra_yaml, steps, warm, voxel=None, feed="async"):
         """feed "async": scans go in through onNewObservation as the reference's data source delivers them
         (LidarOdometry.cpp:162-187: enqueue on the 1-thread pool), as fast as the module takes them (at most 4
         waiting, so the >10-queued drop rule never fires); "sync": each scan is processed on the calling thread
-        before the next one is handed over.  passes > 1: that many timed windows of `steps` scans one after the
-        other on the same module; the MEDIAN window is returned, all of them are kept in run_module.windows."""
+        before the next one is handed over.  Returns (ms, registrations, scans, key-frames) of the timed region."""
         # additive key b200_device: this rank's GPU
         lo = lidar_odometry.LidarOdometry(
             yaml_text=lidar_odometry.system_yaml(voxel_resolution=voxel,
@@ -719,23 +718,17 @@ def run_b200(args, rank, world, local_rank):
             hand_over(s, stamp)
             stamp += 0.1
         lo.wait_idle()
-        windows = []
-        nxt = warm + 1
-        for _ in range(passes):
-            st0 = lo.state()
-            barrier()
-            e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e2.record()
-            for s in range(nxt, nxt + steps):
-                hand_over(s, stamp)
-                stamp += 0.1
-            lo.wait_idle()  # every queued scan and extra-edge registration belongs to the timed region
-            e3.record()
-            barrier()
-            nxt += steps
-            st = lo.state()
-            windows.append((e2.elapsed_time(e3), int(st["n_icp"] - st0["n_icp"]),
-                            int(st["n_processed"] - st0["n_processed"])))
+        st0 = lo.state()
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for s in range(warm + 1, warm + 1 + steps):
+            hand_over(s, stamp)
+            stamp += 0.1
+        lo.wait_idle()  # every queued scan and extra-edge registration belongs to the timed region
+        e3.record()
+        barrier()
+        ms = e2.elapsed_time(e3)
         st = lo.state()
         prof_mod = lo.profile()
         replays["n"] = sum(capi.ICP.profile_of_handle(lo.icp_handle(kind))["graph_replays"] for kind in (0, 1, 2))
@@ -744,9 +737,8 @@ def run_b200(args, rank, world, local_rank):
         sections = {k.replace("doProcessNewObservation.", ""): [round(v[1] / max(v[0], 1) * 1e3, 3), round(v[2] * 1e3, 3)]
                     for k, v in prof_mod.items() if v[0] > 0 and not k.startswith("exception") and v[1] > 1e-5}
         log(f"[bench] module sections, [mean, max] ms per call over {n_all} scans:", json.dumps(sections))
-        run_module.windows = [w[0] for w in windows]
-        ms, regs, scans_done = sorted(windows)[len(windows) // 2]
-        return ms, regs, scans_done, int(st["n_keyframes"])
+        return ms, int(st["n_icp"] - st0["n_icp"]), int(st["n_processed"] - st0["n_processed"]), \
+            int(st["n_keyframes"])
 
     # the headline leg: the same K scans three times, each time through a fresh module, the median run reported (a
     # rare stall of some tens of milliseconds -- all the module's threads at once -- otherwise decides a

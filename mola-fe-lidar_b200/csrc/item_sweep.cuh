@@ -1,5 +1,9 @@
-// item_sweep.cuh -- the search stage: one warp SWEEPS the points around its
-// item instead of every lane walking cells on its own.
+// item_sweep.cuh -- the search stage of BATCHED launches (8 or more jobs in one
+// launch: Monte-Carlo loop, loop-closure candidates; align.cu launch_search_k):
+// one warp SWEEPS the points around its item instead of every lane walking cells
+// on its own.  Converged and lighter in instructions than the walk
+// (tile_search.cuh), which stays the stage of single jobs, where a launch is one
+// wave of items and lasts as long as its slowest item.
 //
 // An item is 32 spatially compact queries (one per lane: consecutive points of
 // the local cloud's own cell-sorted order).  The warp works in PASSES; a pass

@@ -1,6 +1,7 @@
 // Drives the mp2p_icp adapters the way LidarOdometry.cpp:57-88 and 869-880 drive an ICP object:
 // class factory by name -> initialize_solvers/matchers/quality_evaluators -> align(); against the mock
 // upstream headers and the device test double.  Prints one line per check; exit code 0 = all passed.
+#include <mola_b200/FilterEdgesPlanes_B200.h>
 #include <mola_b200/ICP_B200.h>
 #include <mola_b200/Matcher_B200.h>
 #include <mp2p_icp/Matcher_Point2Plane.h>
@@ -13,6 +14,7 @@ using mrpt::containers::yaml;
 extern "C" unsigned long fake_align_calls(void);
 extern "C" unsigned long fake_upload_calls(void);
 extern "C" unsigned long fake_last_call_max_iterations(void);
+extern "C" const b200icp_edges_planes_params_t* fake_last_edges_planes_params(void);
 
 static int g_fail = 0;
 #define CHECK(cond)                                                       \
@@ -142,6 +144,27 @@ int main()
         const auto& p0 = pr.paired_pt2pl[0];
         CHECK(std::fabs(p0.pl_global.centroid.x - (1.5 + 0.1)) < 1e-6 && p0.pt_local.x == 1.5f);
         CHECK(p0.pl_global.plane.coefs[2] == 1.0 && std::fabs(p0.pl_global.plane.coefs[3] + p0.pl_global.centroid.z) < 1e-12);
+    }
+    // --- FilterEdgesPlanes_B200 in the filter pipeline (cpp:139-140, 223-224)
+    {
+        auto f = mrpt::ptr_cast<mp2p_icp_filters::FilterBase>::from(mrpt::rtti::classFactory("mola::FilterEdgesPlanes_B200"));
+        CHECK(f != nullptr);
+        yaml fp = yaml::Map();
+        fp["voxel_filter_resolution"] = yaml(0.5), fp["voxel_filter_decimation"] = yaml(2);
+        fp["voxel_filter_min_e2_e0"] = yaml(100);
+        f->initialize(fp);
+        mp2p_icp::metric_map_t m = to;  // a map with the "raw" layer
+        const std::size_t n = m.point_layer("raw")->size();
+        mp2p_icp_filters::apply_filter_pipeline({f}, m);
+        CHECK(m.point_layer("edges")->size() == n / 4 && m.point_layer("planes")->size() == n / 3 &&
+              m.point_layer("full_decim")->size() == n / 2 && m.point_layer("raw")->size() == n);
+        const auto* ep = fake_last_edges_planes_params();
+        CHECK(ep->voxel_filter_resolution == 0.5f && ep->voxel_filter_decimation == 2 && ep->voxel_filter_min_e2_e0 == 100.f);
+        CHECK(ep->full_pointcloud_decimation == 10 && ep->voxel_filter_max_e2_e0 == 30.f);  // the shipped defaults
+        mp2p_icp::metric_map_t empty_map;
+        bool threw = false;
+        try { f->filter(empty_map); } catch (const std::exception&) { threw = true; }
+        CHECK(threw);  // no input layer
     }
     std::printf("%s (%d failed)\n", g_fail ? "FAILED" : "ALL OK", g_fail);
     return g_fail ? 1 : 0;

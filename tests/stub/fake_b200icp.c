@@ -98,6 +98,32 @@ int b200icp_voxel_decimate(b200icp_t* icp, const b200icp_cloud_t* in, float reso
     g_voxel_calls++;
     return B200ICP_OK;
 }
+/* "FilterEdgesPlanes": layers of n/4, n/3 and n/2 points, visible at the seam; the parameters are recorded */
+static b200icp_edges_planes_params_t g_last_ep;
+const b200icp_edges_planes_params_t* fake_last_edges_planes_params(void) { return &g_last_ep; }
+void b200icp_edges_planes_defaults(b200icp_edges_planes_params_t* p)
+{
+    p->voxel_filter_resolution = 1.0f, p->full_pointcloud_decimation = 10, p->voxel_filter_decimation = 10;
+    p->voxel_filter_max_e2_e0 = 30.f, p->voxel_filter_max_e1_e0 = 30.f;
+    p->voxel_filter_min_e2_e0 = 80.f, p->voxel_filter_min_e1_e0 = 80.f, p->min_points_per_voxel = 5;
+}
+int b200icp_filter_edges_planes(b200icp_t* icp, const b200icp_cloud_t* in, const b200icp_edges_planes_params_t* params,
+                                float search_radius, b200icp_cloud_t* layers_out[3], uint8_t* layer_flags_out,
+                                uint32_t* n_classified_voxels_out)
+{
+    (void)icp, (void)search_radius, (void)layer_flags_out;
+    g_last_ep = *params;
+    const size_t div[3] = {4, 3, 2};
+    for (int l = 0; l < 3; l++)
+    {
+        b200icp_cloud_t* c = (b200icp_cloud_t*)calloc(1, sizeof(*c));
+        *c = *in;
+        c->n = in->n / div[l];
+        layers_out[l] = c;
+    }
+    if (n_classified_voxels_out) *n_classified_voxels_out = 1;
+    return B200ICP_OK;
+}
 static void fake_result(const b200icp_cloud_t* from, const b200icp_cloud_t* to, const double* guess,
                         b200icp_result_t* r)
 {

@@ -17,7 +17,8 @@ def driver(tmp_path_factory):
     fake = str(d / "libfake_b200icp.so")
     subprocess.check_call(["gcc", "-O1", "-shared", "-fPIC", "-o", fake, os.path.join(ROOT, "tests", "stub", "fake_b200icp.c")])
     exe = str(d / "adapter_driver")
-    srcs = [os.path.join(AD, "src", f) for f in ("DeviceCloudCache.cpp", "ICP_B200.cpp", "Matcher_B200.cpp", "register.cpp")]
+    srcs = [os.path.join(AD, "src", f) for f in ("DeviceCloudCache.cpp", "ICP_B200.cpp", "Matcher_B200.cpp",
+                                                  "FilterEdgesPlanes_B200.cpp", "register.cpp")]
     srcs += [os.path.join(ROOT, "tests", "mock_upstream", "mp2p_icp", "mock_register.cpp"),
              os.path.join(ROOT, "tests", "stub", "adapter_driver.cpp")]
     subprocess.check_call([CXX, "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-pthread",
@@ -37,7 +38,8 @@ def test_adapters_compile_warning_free_and_drive_the_icp_seam(driver):
 def test_cmake_project_is_guarded_by_find_package():
     txt = open(os.path.join(AD, "CMakeLists.txt")).read()
     assert "find_package(mp2p_icp QUIET)" in txt and "return()" in txt
-    for f in ("src/DeviceCloudCache.cpp", "src/ICP_B200.cpp", "src/Matcher_B200.cpp", "src/register.cpp"):
+    for f in ("src/DeviceCloudCache.cpp", "src/ICP_B200.cpp", "src/Matcher_B200.cpp", "src/FilterEdgesPlanes_B200.cpp",
+              "src/register.cpp"):
         assert f in txt and os.path.exists(os.path.join(AD, f))
 
 

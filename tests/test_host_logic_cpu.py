@@ -128,6 +128,43 @@ def test_voxel_stage_from_pointcloud_filter_block(fake_lib):
     assert r["voxel_calls"] == 3 and r["last_points_size"] == 50 and float(r["res"]) == 1.0
 
 
+def test_edges_planes_stage_from_pointcloud_filter_block(fake_lib):
+    """`pointcloud_filter: - class_name: ...FilterEdgesPlanes` (the class the reference's stale keys name,
+    kitti-default.yaml:21-32): parsed with the shipped defaults, the configured layer is what gets registered
+    (the double returns layers of n/4, n/3 and n/2 points), unknown layers / classes are refused."""
+    r = run_child(fake_lib, """
+        def block(cls, layer):
+            return ("  pointcloud_filter:\\n"
+                    "    - class_name: " + cls + "\\n"
+                    "      params:\\n"
+                    "        voxel_filter_resolution: 0.5\\n"
+                    "        voxel_filter_decimation: 2\\n"
+                    "        b200_register_layer: " + layer + "\\n")
+        sizes = {}
+        for cls, layer in (("mp2p_icp_filters::FilterEdgesPlanes", "edges"),
+                           ("mola::lidar_segmentation::FilterEdgesPlanes", "planes"),
+                           ("mp2p_icp_filters::FilterEdgesPlanes", "full_decim")):
+            lo = lom.LidarOdometry(yaml_text=lom.system_yaml(extra=block(cls, layer)))
+            for i in range(2):
+                lo.onNewObservation(scan(float(i), n=120), 0.1 * i, sync=True)
+            sizes[layer] = int(lo.state()["last_points_size"])
+            out["n_icp_" + layer] = int(lo.state()["n_icp"])
+            lo.close()
+        out["sizes"] = sizes
+        errs = []
+        for cls, layer in (("mp2p_icp_filters::FilterEdgesPlanes", "corners"), ("mp2p_icp_filters::FilterNoSuch", "edges")):
+            try:
+                lom.LidarOdometry(yaml_text=lom.system_yaml(extra=block(cls, layer)))
+                errs.append("")
+            except Exception as e:
+                errs.append(str(e))
+        out["errs"] = errs
+    """)
+    assert r["sizes"] == {"edges": 30, "planes": 40, "full_decim": 60}
+    assert r["n_icp_edges"] == 1 and r["n_icp_planes"] == 1 and r["n_icp_full_decim"] == 1
+    assert "b200_register_layer" in r["errs"][0] and "not registered" in r["errs"][1]
+
+
 def test_async_queue_and_extra_edges_use_batch_api(fake_lib):
     """onNewObservation is asynchronous (1-thread pool, cpp:183-184); the extra
     nearby / loop-closure edges run on the second pool (cpp:711-729) and the
